@@ -1,0 +1,138 @@
+/*
+ * ouzelum_b200 -- C ABI of the B200-native quadcopter env-step path.
+ *
+ * This is the drop-in boundary: what the reference reaches through the Isaac Gym pybind API
+ * (gymapi / gymtorch -- a closed binary that is NOT under the reference tree) plus the eager
+ * torch ops around it.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are ordinary pointers into CUDA global memory that the
+ *     CALLER owns (torch tensors on the Python side: pass tensor.data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  No entry point on
+ *     the step path synchronises with the host or allocates; everything is CUDA-graph capturable.
+ *   - every function returns 0 on success, non-zero on error; ozl_last_error() returns a
+ *     thread-local message for the last failing call.
+ *   - quaternions in root states are xyzw (Isaac Gym); linear AND angular velocity are world-frame.
+ *   - handles are not thread-safe; distinct handles are independent.  One process per GPU.
+ */
+#ifndef OUZELUM_B200_H
+#define OUZELUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OZL_ABI_VERSION 1
+
+/* sensor-fault model of isaacgymenvs/utils/POMDP.py:4-42 */
+enum { OZL_POMDP_NONE = 0, OZL_POMDP_FLICKER = 1, OZL_POMDP_NOISE = 2, OZL_POMDP_FLICKER_NOISE = 3 };
+
+/* Task configuration.  Defaults (ozl_cfg_default) reproduce isaacgymenvs/cfg/task/Ouzelum.yaml and
+ * the literals in isaacgymenvs/tasks/ouzelum.py; the "extras" are zero-default options with no
+ * reference counterpart. */
+typedef struct ozl_cfg {
+    int32_t abi_version;          /* must be OZL_ABI_VERSION */
+    int32_t reserved0;
+    int64_t num_envs;             /* envs simulated by THIS handle (the local shard)            cfg env.numEnvs */
+    int64_t env_id_base;          /* global id of local env 0: RNG is keyed by global id, so results do not depend on the sharding */
+    uint64_t seed;
+    int32_t max_episode_length;   /* env.maxEpisodeLength (2000)                                  Ouzelum.yaml:10 */
+    int32_t target_period;        /* resample the target when progress % period == 0 (500)        ouzelum.py:221  */
+    int32_t target_fixed;         /* 1: never resample (landing-family tasks drive the target)                    */
+    int32_t substeps;             /* sim.substeps (2)                                             Ouzelum.yaml:21 */
+    int32_t control_freq_inv;     /* env.controlFrequencyInv (1)                                  vec_task.py:100 */
+    float dt;                     /* sim.dt (0.01)                                                Ouzelum.yaml:20 */
+    float gravity_z;              /* -9.81                                                        ouzelum.py:118  */
+    float clip_actions;           /* env.clipActions (1.0)                                        vec_task.py:327 */
+    float clip_obs;               /* env.clipObservations (5.0)                                   vec_task.py:353 */
+    float thrust_rate;            /* dt * 2000                                                    ouzelum.py:237  */
+    float thrust_max;             /* 2000                                                         ouzelum.py:91   */
+    float die_dist;               /* 8.0                                                          ouzelum.py:326  */
+    float die_z;                  /* 0.5 (0.3 for the landing family)                             ouzelum.py:327  */
+    float up_coef;                /* 5.0 (1.0 for Quadcopter)                                     ouzelum.py:314  */
+    float spawn_base[3];          /* (0,0,1)                                                      ouzelum.py:150  */
+    float spawn_lo[3];            /* (-1.5,-1.5,-0.2)                                             ouzelum.py:207  */
+    float spawn_range[3];         /* (3.0,3.0,1.7)                                                                */
+    float target_scale[3];        /* (10,10,1)                                                    ouzelum.py:183  */
+    float target_off[3];          /* (-5,-5,1)                                                                    */
+    /* single-rigid-body x500 (assets/x500/x500.urdf) */
+    float mass, ixx, iyy, izz, arm, com_z, max_angvel;
+    /* extras (no reference counterpart; 0 => reference behaviour) */
+    float lin_drag;               /* F = -k v (world)                                                             */
+    float yaw_km;                 /* rotor reaction torque about body z per newton of thrust                      */
+    int32_t fault_mode;           /* 1: single-rotor loss of effectiveness, schedule drawn at reset               */
+    float fault_eff_lo, fault_eff_range;
+    int32_t dr_enable;            /* 1: mass/Ixx/Iyy/Izz/arm/thrust-scale *= U[dr_lo, dr_lo+dr_range) at reset    */
+    float dr_lo, dr_range;        /*    (schema of isaacgymenvs/utils/dr_utils.py:121-130: scaling, uniform)      */
+    int32_t pomdp_mode;           /* OZL_POMDP_* applied to the observation inside the step (tasks/landed.py:340) */
+    float pomdp_prob;             /* flicker probability                                          POMDP.py:8      */
+    float noise_sigma;            /* multiplicative noise U(1-s, 1+s)                             POMDP.py:9-10   */
+    int32_t collect_metrics;      /* 1: accumulate the episode/reward metrics vector (ozl_metrics_read)           */
+    int32_t reserved1;
+} ozl_cfg;
+
+typedef struct ozl_env ozl_env;   /* opaque */
+
+/* Fill *cfg with the Ouzelum defaults for `num_envs` envs.  (cfg/task/Ouzelum.yaml, tasks/ouzelum.py:42-99) */
+int ozl_cfg_default(ozl_cfg* cfg, int64_t num_envs);
+
+/* Create the private SoA state for cfg->num_envs envs on CUDA device `device`.
+ * Replaces: VecTask.__init__ -> create_sim/_create_envs (tasks/ouzelum.py:112-178; an O(N) Python loop
+ * of gym.create_env/create_actor) + acquire/wrap of the root-state tensors (tasks/ouzelum.py:59-99). */
+int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out);
+int ozl_destroy(ozl_env* env);
+
+/* Zero all private state (root = initial pose, thrust 0, target (0,0,1)), reset the step counter and
+ * the metrics, and set the RNG seed.  The caller re-initialises its own reset_buf (=1) / progress_buf (=0)
+ * as VecTask.allocate_buffers does (tasks/base/vec_task.py:254-277). */
+int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream);
+
+/* One fused env step == VecTask.step (tasks/base/vec_task.py:313-359) with Ouzelum's hooks
+ * (tasks/ouzelum.py:218-295) and gym.simulate replaced by the in-kernel rigid-body integrator.
+ *   actions  [N,4] f32 in    (clamped to +-clip_actions inside)
+ *   obs      [N,13] f32 out  (already clamped to +-clip_obs, i.e. obs_dict["obs"])
+ *   rew      [N] f32 out
+ *   reset    [N] i64 in/out  (reset_buf: request from the previous step in, new flag out)
+ *   progress [N] i64 in/out  (progress_buf)
+ *   timeout  [N] u8 out      (timeout_buf as bool; may be NULL)
+ *   ep_ret   [N] f32 out     (episode return at episode end, RecordEpisodeStatisticsTorch "r"; may be NULL) */
+int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
+             uint8_t* timeout, float* ep_ret, void* stream);
+
+/* Mode-B throughput entry: K steps in ONE launch, state held in registers, actions a = 2u-1 drawn
+ * in-kernel from the counter RNG; obs/rew are written for the LAST step only, reset/progress are
+ * carried.  No reference counterpart (SURVEY 8d "mode B"). */
+int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int64_t* reset, int64_t* progress, void* stream);
+
+/* State access (row-major AoS device buffers; any pointer may be NULL = skip).
+ * Replaces the aliasing views root_states/thrusts/target_root_positions (tasks/ouzelum.py:67-96). */
+int ozl_get_state(ozl_env* env, float* root13, float* thrust4, float* target3, float* ep_ret, void* stream);
+int ozl_set_state(ozl_env* env, const float* root13, const float* thrust4, const float* target3,
+                  const float* ep_ret, void* stream);
+/* per-env parameters: params7 [N,7] = mass, ixx, iyy, izz, arm, thrust_scale, fault_effectiveness;
+ * fault2 [N,2] i32 = fault rotor id, fault onset step (>= 2^29: never). */
+int ozl_get_params(ozl_env* env, float* params7, int32_t* fault2, void* stream);
+int ozl_set_params(ozl_env* env, const float* params7, const int32_t* fault2, void* stream);
+
+/* Step counter (the RNG's time axis): number of ozl_step's since ozl_reset_all.  Host-synchronising. */
+int ozl_get_step_count(ozl_env* env, uint64_t* out, void* stream);
+int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream);
+
+/* Metrics vector accumulated since the last clearing read (16 doubles, device pointer `out16`):
+ *  [0] sum reward  [1] sum episode return of finished episodes  [2..7] reserved
+ *  [8] env-steps  [9] finished episodes  [10] sum of finished episode lengths  [11] time-outs
+ *  [12] dist>die_dist  [13] z<die_z  [14] env-steps with an active rotor fault  [15] resets applied
+ * Replaces RecordEpisodeStatisticsTorch + the trainer's Python scan (RPO-LSTM/utils.py:20-35, main.py:105-113). */
+int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream);
+
+const char* ozl_last_error(void);
+int ozl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OUZELUM_B200_H */

@@ -1,0 +1,113 @@
+"""ctypes binding of libouzelum_b200.so (the C ABI declared in include/ouzelum_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing the package
+raises.  Build it with `python __graft_entry__.py` (or `python -m ouzelum_b200.build`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libouzelum_b200.so")
+
+OZL_ABI_VERSION = 1
+
+
+class OzlCfg(C.Structure):
+    """Mirror of `struct ozl_cfg` (include/ouzelum_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("reserved0", C.c_int32),
+        ("num_envs", C.c_int64), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
+        ("max_episode_length", C.c_int32), ("target_period", C.c_int32), ("target_fixed", C.c_int32),
+        ("substeps", C.c_int32), ("control_freq_inv", C.c_int32),
+        ("dt", C.c_float), ("gravity_z", C.c_float), ("clip_actions", C.c_float), ("clip_obs", C.c_float),
+        ("thrust_rate", C.c_float), ("thrust_max", C.c_float),
+        ("die_dist", C.c_float), ("die_z", C.c_float), ("up_coef", C.c_float),
+        ("spawn_base", C.c_float * 3), ("spawn_lo", C.c_float * 3), ("spawn_range", C.c_float * 3),
+        ("target_scale", C.c_float * 3), ("target_off", C.c_float * 3),
+        ("mass", C.c_float), ("ixx", C.c_float), ("iyy", C.c_float), ("izz", C.c_float),
+        ("arm", C.c_float), ("com_z", C.c_float), ("max_angvel", C.c_float),
+        ("lin_drag", C.c_float), ("yaw_km", C.c_float),
+        ("fault_mode", C.c_int32), ("fault_eff_lo", C.c_float), ("fault_eff_range", C.c_float),
+        ("dr_enable", C.c_int32), ("dr_lo", C.c_float), ("dr_range", C.c_float),
+        ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float), ("noise_sigma", C.c_float),
+        ("collect_metrics", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+    def to_dict(self):
+        out = {}
+        for name, typ in self._fields_:
+            if name.startswith("reserved") or name == "abi_version":
+                continue
+            v = getattr(self, name)
+            out[name] = tuple(v) if hasattr(v, "__len__") else v
+        return out
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if k not in dict(self._fields_):
+                raise KeyError(f"ozl_cfg has no field {k!r}")
+            if isinstance(v, (tuple, list)):
+                getattr(self, k)[:] = [float(x) for x in v]
+            else:
+                setattr(self, k, v)
+        return self
+
+
+_P = C.c_void_p
+_SIGS = {
+    "ozl_abi_version": (C.c_int, []),
+    "ozl_last_error": (C.c_char_p, []),
+    "ozl_cfg_default": (C.c_int, [C.POINTER(OzlCfg), C.c_int64]),
+    "ozl_create": (C.c_int, [C.POINTER(OzlCfg), C.c_int, C.POINTER(_P)]),
+    "ozl_destroy": (C.c_int, [_P]),
+    "ozl_reset_all": (C.c_int, [_P, C.c_uint64, _P]),
+    "ozl_step": (C.c_int, [_P] * 9),
+    "ozl_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ozl_get_state": (C.c_int, [_P] * 6),
+    "ozl_set_state": (C.c_int, [_P] * 6),
+    "ozl_get_params": (C.c_int, [_P] * 4),
+    "ozl_set_params": (C.c_int, [_P] * 4),
+    "ozl_get_step_count": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
+    "ozl_set_step_count": (C.c_int, [_P, C.c_uint64, _P]),
+    "ozl_metrics_read": (C.c_int, [_P, _P, C.c_int32, _P]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"ouzelum_b200: native library {LIB_PATH} is missing. This framework has no CPU/PyTorch fallback; "
+            "build it with `python -c 'import __graft_entry__ as g; g.build()'` from the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)        # AttributeError if the .so is stale -> loud
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.ozl_abi_version()
+    if v != OZL_ABI_VERSION:
+        raise RuntimeError(f"ouzelum_b200: library ABI {v} != binding ABI {OZL_ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return (lib.ozl_last_error() or b"").decode()
+
+
+def check(rc, exc=RuntimeError):
+    if rc != 0:
+        raise exc(f"ouzelum_b200: {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def default_cfg(num_envs, **over):
+    cfg = OzlCfg()
+    check(lib.ozl_cfg_default(C.byref(cfg), int(num_envs)))
+    cfg.update(**over)
+    return cfg

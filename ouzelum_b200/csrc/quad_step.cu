@@ -1,0 +1,571 @@
+// K1 `quad_step`: the fused x500 env step, one env per thread, for sm_100a.
+// Host-side twin of the arithmetic: oracle/quad_step.py.  Layout + roofline: DESIGN.md.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "internal.h"
+
+namespace ozl {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return set_error("%s: %s", what, cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------------ plane I/O
+struct Loaded {
+    float4 d0, d1, d2, d3, s0, s1, s2;
+    float2 d4;
+};
+
+__device__ __forceinline__ void unpack(const Loaded& L, Env& e) {
+    e.p[0] = L.d0.x; e.p[1] = L.d0.y; e.p[2] = L.d0.z;
+    e.q[0] = L.d0.w; e.q[1] = L.d1.x; e.q[2] = L.d1.y; e.q[3] = L.d1.z;
+    e.v[0] = L.d1.w; e.v[1] = L.d2.x; e.v[2] = L.d2.y;
+    e.w[0] = L.d2.z; e.w[1] = L.d2.w; e.w[2] = L.d3.x;
+    e.T[0] = L.d3.y; e.T[1] = L.d3.z; e.T[2] = L.d3.w; e.T[3] = L.d4.x;
+    e.ep_ret = L.d4.y;
+    e.tgt[0] = L.s0.x; e.tgt[1] = L.s0.y; e.tgt[2] = L.s0.z; e.eff = L.s0.w;
+    e.mass = L.s1.x; e.ixx = L.s1.y; e.iyy = L.s1.z; e.izz = L.s1.w;
+    e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z);
+}
+__device__ __forceinline__ void load_env(const Planes& pl, int64_t i, Loaded& L) {
+    L.d0 = pl.d0[i]; L.d1 = pl.d1[i]; L.d2 = pl.d2[i]; L.d3 = pl.d3[i]; L.d4 = pl.d4[i];
+    L.s0 = pl.s0[i]; L.s1 = pl.s1[i]; L.s2 = pl.s2[i];
+}
+__device__ __forceinline__ void store_dynamic(const Planes& pl, int64_t i, const Env& e) {
+    pl.d0[i] = make_float4(e.p[0], e.p[1], e.p[2], e.q[0]);
+    pl.d1[i] = make_float4(e.q[1], e.q[2], e.q[3], e.v[0]);
+    pl.d2[i] = make_float4(e.v[1], e.v[2], e.w[0], e.w[1]);
+    pl.d3[i] = make_float4(e.w[2], e.T[0], e.T[1], e.T[2]);
+    pl.d4[i] = make_float2(e.T[3], e.ep_ret);
+}
+__device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const Env& e) {
+    pl.s0[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
+    pl.s1[i] = make_float4(e.mass, e.ixx, e.iyy, e.izz);
+    pl.s2[i] = make_float4(e.arm, e.ks, __uint_as_float(e.fault), 0.0f);
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Per-block metric reduction (K6): ballots/shuffles per warp -> smem -> one atomic per metric per block
+// into the block's slot.  Then the last block to finish (ticket) advances the step counter.
+template <int BLOCK>
+__device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl, bool valid, const StepOut& o,
+                                               uint64_t step, uint32_t step_inc, double (*s_m)[10]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (c.collect_metrics) {
+        const unsigned full = 0xffffffffu;
+        const bool done = valid && o.reset;
+        const double srew = warp_sum(valid ? (double)o.rew : 0.0);
+        const double sret = warp_sum(done ? (double)o.ep_ret_done : 0.0);
+        const int slen = __reduce_add_sync(full, done ? (int)o.prog : 0);
+        const int n_valid = __popc(__ballot_sync(full, valid));
+        const int n_done = __popc(__ballot_sync(full, done));
+        const int n_to = __popc(__ballot_sync(full, valid && o.timeout));
+        const int n_cd = __popc(__ballot_sync(full, valid && o.crash_dist));
+        const int n_cz = __popc(__ballot_sync(full, valid && o.crash_z));
+        const int n_fa = __popc(__ballot_sync(full, valid && o.fault_active));
+        const int n_rs = __popc(__ballot_sync(full, valid && o.did_reset));
+        if (lane == 0) {
+            s_m[warp][0] = srew; s_m[warp][1] = sret; s_m[warp][2] = n_valid; s_m[warp][3] = n_done;
+            s_m[warp][4] = slen; s_m[warp][5] = n_to; s_m[warp][6] = n_cd; s_m[warp][7] = n_cz;
+            s_m[warp][8] = n_fa; s_m[warp][9] = n_rs;
+        }
+        __syncthreads();
+        if (threadIdx.x < 10) {
+            double v = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < BLOCK / 32; ++wv) v += s_m[wv][threadIdx.x];
+            const int idx = threadIdx.x < 2 ? threadIdx.x : threadIdx.x + 6;   // sums at [0,1], counts at [8..15]
+            if (v != 0.0) atomicAdd(pl.metrics + (blockIdx.x % kMetricSlots) * kMetricStride + idx, v);
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd(pl.ctrl + 1, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1ull) {   // every other block has already read ctrl[0]
+            pl.ctrl[1] = 0ull;
+            pl.ctrl[0] = step + step_inc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
+                 float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
+                 uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out) {
+    __shared__ __align__(16) float s_obs[BLOCK * 13];
+    __shared__ double s_m[BLOCK / 32][10];
+
+    const int64_t base = (int64_t)blockIdx.x * BLOCK;
+    const int64_t i = base + threadIdx.x;
+    const bool valid = i < c.num_envs;
+    const uint64_t step = ld_relaxed(pl.ctrl);
+
+    StepOut o;
+    o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
+    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = false;
+
+    if (valid) {
+        // all loads issued up front: 9 x 128-bit + 2 x 64-bit per env in flight
+        Loaded L;
+        load_env(pl, i, L);
+        const float4 a4 = __ldg(actions + i);
+        const int64_t prog = progress[i];
+        const bool rst = reset[i] != 0;
+        Env e;
+        unpack(L, e);
+        const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+        const uint32_t genv = c.env_id_base + (uint32_t)i;
+        env_step(e, act, prog, rst, genv, step, c, o);
+        obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
+
+        store_dynamic(pl, i, e);
+        if (o.static_dirty) store_static(pl, i, e);
+        rew[i] = o.rew;
+        reset[i] = o.reset ? 1 : 0;
+        progress[i] = o.prog;
+        if (timeout) timeout[i] = o.timeout ? 1 : 0;
+        if (ep_ret_out) ep_ret_out[i] = o.ep_ret_done;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) s_obs[threadIdx.x * 13 + j] = o.obs[j];   // stride 13: conflict-free
+    }
+    __syncthreads();
+    // [N,13] row-major observation tile of this block is contiguous: write it with full 16-byte lanes
+    {
+        const int64_t remaining = c.num_envs - base;
+        const int n_here = remaining < BLOCK ? (int)remaining : BLOCK;
+        float* dst = obs + base * 13;
+        const int nflt = n_here * 13;
+        if ((nflt & 3) == 0) {   // base*13*4 bytes is 16-byte aligned whenever BLOCK % 4 == 0
+            float4* d4p = reinterpret_cast<float4*>(dst);
+            const float4* s4 = reinterpret_cast<const float4*>(s_obs);
+            for (int k = threadIdx.x; k < nflt / 4; k += BLOCK) d4p[k] = s4[k];
+        } else {
+            for (int k = threadIdx.x; k < nflt; k += BLOCK) dst[k] = s_obs[k];
+        }
+    }
+    block_epilogue<BLOCK>(c, pl, valid, o, step, 1u, s_m);
+}
+
+// ------------------------------------------------------------------------------------------------ mode B
+// K steps per launch with the env in registers; actions a = 2u-1 from the counter RNG.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+quad_rollout_kernel(const DevCfg c, const Planes pl, int K, float* __restrict__ obs, float* __restrict__ rew,
+                    int64_t* __restrict__ reset, int64_t* __restrict__ progress) {
+    __shared__ double s_m[BLOCK / 32][10];
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool valid = i < c.num_envs;
+    const uint64_t step0 = ld_relaxed(pl.ctrl);
+    StepOut o;
+    o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
+    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = false;
+    Env e;
+    int64_t prog = 0;
+    bool rst = false, dirty = false;
+    const uint32_t genv = c.env_id_base + (uint32_t)i;
+    if (valid) {
+        Loaded L;
+        load_env(pl, i, L);
+        unpack(L, e);
+        prog = progress[i];
+        rst = reset[i] != 0;
+    }
+    for (int k = 0; k < K; ++k) {
+        const uint64_t step = step0 + (uint64_t)k;
+        if (valid) {
+            const uint4 r = draw(c.seed, genv, step, P_ACTION);
+            const float act[4] = {2.0f * u01(r.x) - 1.0f, 2.0f * u01(r.y) - 1.0f, 2.0f * u01(r.z) - 1.0f,
+                                  2.0f * u01(r.w) - 1.0f};
+            env_step(e, act, prog, rst, genv, step, c, o);
+            prog = o.prog;
+            rst = o.reset;
+            dirty = dirty || o.static_dirty;
+        }
+        if (k + 1 < K && c.collect_metrics) {
+            // metrics for the intermediate steps (the last step goes through block_epilogue)
+            // -- same reduction, without the ticket
+            const int lane = threadIdx.x & 31;
+            const bool done = valid && o.reset;
+            const double srew = warp_sum(valid ? (double)o.rew : 0.0);
+            const double sret = warp_sum(done ? (double)o.ep_ret_done : 0.0);
+            const int slen = __reduce_add_sync(0xffffffffu, done ? (int)o.prog : 0);
+            const int cnt[7] = {__popc(__ballot_sync(0xffffffffu, valid)), __popc(__ballot_sync(0xffffffffu, done)), slen,
+                                __popc(__ballot_sync(0xffffffffu, valid && o.timeout)),
+                                __popc(__ballot_sync(0xffffffffu, valid && o.crash_dist)),
+                                __popc(__ballot_sync(0xffffffffu, valid && o.crash_z)),
+                                __popc(__ballot_sync(0xffffffffu, valid && o.fault_active))};
+            const int n_rs = __popc(__ballot_sync(0xffffffffu, valid && o.did_reset));
+            if (lane == 0) {
+                double* m = pl.metrics + (blockIdx.x % kMetricSlots) * kMetricStride;
+                if (srew != 0.0) atomicAdd(m + 0, srew);
+                if (sret != 0.0) atomicAdd(m + 1, sret);
+#pragma unroll
+                for (int j = 0; j < 7; ++j)
+                    if (cnt[j]) atomicAdd(m + 8 + j, (double)cnt[j]);
+                if (n_rs) atomicAdd(m + 15, (double)n_rs);
+            }
+        }
+    }
+    if (valid) {
+        obs_epilogue(o.obs, genv, step0 + (uint64_t)(K - 1), flicker_blackout(step0 + (uint64_t)(K - 1), c), c);
+        store_dynamic(pl, i, e);
+        if (dirty) store_static(pl, i, e);
+        rew[i] = o.rew;
+        reset[i] = o.reset ? 1 : 0;
+        progress[i] = o.prog;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) obs[i * 13 + j] = o.obs[j];
+    }
+    block_epilogue<BLOCK>(c, pl, valid, o, step0, (uint32_t)K, s_m);
+}
+
+// ------------------------------------------------------------------------------------------------ state access
+__global__ void get_state_kernel(const Planes pl, int64_t n, float* root13, float* thrust4, float* target3, float* ep_ret) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Loaded L;
+    load_env(pl, i, L);
+    Env e;
+    unpack(L, e);
+    if (root13) {
+        float* r = root13 + i * 13;
+        r[0] = e.p[0]; r[1] = e.p[1]; r[2] = e.p[2];
+        r[3] = e.q[0]; r[4] = e.q[1]; r[5] = e.q[2]; r[6] = e.q[3];
+        r[7] = e.v[0]; r[8] = e.v[1]; r[9] = e.v[2];
+        r[10] = e.w[0]; r[11] = e.w[1]; r[12] = e.w[2];
+    }
+    if (thrust4) { float* t = thrust4 + i * 4; t[0] = e.T[0]; t[1] = e.T[1]; t[2] = e.T[2]; t[3] = e.T[3]; }
+    if (target3) { float* t = target3 + i * 3; t[0] = e.tgt[0]; t[1] = e.tgt[1]; t[2] = e.tgt[2]; }
+    if (ep_ret) ep_ret[i] = e.ep_ret;
+}
+
+__global__ void set_state_kernel(const Planes pl, int64_t n, const float* root13, const float* thrust4,
+                                 const float* target3, const float* ep_ret) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Loaded L;
+    load_env(pl, i, L);
+    Env e;
+    unpack(L, e);
+    if (root13) {
+        const float* r = root13 + i * 13;
+        e.p[0] = r[0]; e.p[1] = r[1]; e.p[2] = r[2];
+        e.q[0] = r[3]; e.q[1] = r[4]; e.q[2] = r[5]; e.q[3] = r[6];
+        e.v[0] = r[7]; e.v[1] = r[8]; e.v[2] = r[9];
+        e.w[0] = r[10]; e.w[1] = r[11]; e.w[2] = r[12];
+    }
+    if (thrust4) { const float* t = thrust4 + i * 4; e.T[0] = t[0]; e.T[1] = t[1]; e.T[2] = t[2]; e.T[3] = t[3]; }
+    if (target3) { const float* t = target3 + i * 3; e.tgt[0] = t[0]; e.tgt[1] = t[1]; e.tgt[2] = t[2]; }
+    if (ep_ret) e.ep_ret = ep_ret[i];
+    store_dynamic(pl, i, e);
+    store_static(pl, i, e);
+}
+
+__global__ void get_params_kernel(const Planes pl, int64_t n, float* params7, int32_t* fault2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Loaded L;
+    load_env(pl, i, L);
+    Env e;
+    unpack(L, e);
+    if (params7) {
+        float* p = params7 + i * 7;
+        p[0] = e.mass; p[1] = e.ixx; p[2] = e.iyy; p[3] = e.izz; p[4] = e.arm; p[5] = e.ks; p[6] = e.eff;
+    }
+    if (fault2) { fault2[i * 2] = (int32_t)(e.fault & 3u); fault2[i * 2 + 1] = (int32_t)(e.fault >> 2); }
+}
+
+__global__ void set_params_kernel(const Planes pl, int64_t n, const float* params7, const int32_t* fault2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Loaded L;
+    load_env(pl, i, L);
+    Env e;
+    unpack(L, e);
+    if (params7) {
+        const float* p = params7 + i * 7;
+        e.mass = p[0]; e.ixx = p[1]; e.iyy = p[2]; e.izz = p[3]; e.arm = p[4]; e.ks = p[5]; e.eff = p[6];
+    }
+    if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | ((uint32_t)fault2[i * 2 + 1] << 2);
+    store_static(pl, i, e);
+}
+
+__global__ void init_state_kernel(const DevCfg c, const Planes pl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { pl.ctrl[0] = 0ull; pl.ctrl[1] = 0ull; }
+    if (i < kMetricSlots * kMetricStride) pl.metrics[i] = 0.0;
+    if (i >= c.num_envs) return;
+    Env e;
+    e.p[0] = c.spawn_base[0]; e.p[1] = c.spawn_base[1]; e.p[2] = c.spawn_base[2];
+    e.q[0] = e.q[1] = e.q[2] = 0.0f; e.q[3] = 1.0f;
+    for (int j = 0; j < 3; ++j) { e.v[j] = 0.0f; e.w[j] = 0.0f; }
+    for (int j = 0; j < 4; ++j) e.T[j] = 0.0f;
+    e.ep_ret = 0.0f;
+    e.tgt[0] = 0.0f; e.tgt[1] = 0.0f; e.tgt[2] = 1.0f;        // ouzelum.py:71-73
+    e.eff = 1.0f;
+    e.mass = c.mass; e.ixx = c.ixx; e.iyy = c.iyy; e.izz = c.izz; e.arm = c.arm; e.ks = 1.0f;
+    e.fault = FAULT_NEVER << 2;
+    store_dynamic(pl, i, e);
+    store_static(pl, i, e);
+}
+
+__global__ void metrics_read_kernel(const Planes pl, double* out16, int clear) {
+    const int j = threadIdx.x;
+    if (j >= 16) return;
+    double v = 0.0;
+    for (int s = 0; s < kMetricSlots; ++s) {
+        v += pl.metrics[s * kMetricStride + j];
+        if (clear) pl.metrics[s * kMetricStride + j] = 0.0;
+    }
+    out16[j] = v;
+}
+
+__global__ void set_step_kernel(const Planes pl, unsigned long long v) { pl.ctrl[0] = v; pl.ctrl[1] = 0ull; }
+
+}  // namespace ozl
+
+using namespace ozl;
+
+// ------------------------------------------------------------------------------------------------ host: cfg
+static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
+    memset(&d, 0, sizeof(d));
+    d.num_envs = c.num_envs;
+    d.seed = c.seed;
+    d.env_id_base = (uint32_t)c.env_id_base;
+    d.max_episode_length = c.max_episode_length;
+    d.target_period = c.target_period;
+    d.target_fixed = c.target_fixed;
+    d.nsub = c.substeps * c.control_freq_inv;
+    d.fault_mode = c.fault_mode;
+    d.dr_enable = c.dr_enable;
+    d.pomdp_mode = c.pomdp_mode;
+    d.collect_metrics = c.collect_metrics;
+    d.clip_actions = c.clip_actions; d.clip_obs = c.clip_obs;
+    d.thrust_rate = c.thrust_rate; d.thrust_max = c.thrust_max;
+    d.die_dist = c.die_dist; d.die_z = c.die_z; d.up_coef = c.up_coef;
+    for (int j = 0; j < 3; ++j) {
+        d.spawn_base[j] = c.spawn_base[j]; d.spawn_lo[j] = c.spawn_lo[j]; d.spawn_range[j] = c.spawn_range[j];
+        d.target_scale[j] = c.target_scale[j]; d.target_off[j] = c.target_off[j];
+    }
+    d.mass = c.mass; d.ixx = c.ixx; d.iyy = c.iyy; d.izz = c.izz; d.arm = c.arm; d.com_z = c.com_z;
+    d.max_angvel = c.max_angvel;
+    d.max_angvel2 = (float)((double)c.max_angvel * (double)c.max_angvel);
+    d.lin_drag = c.lin_drag; d.yaw_km = c.yaw_km; d.gravity_z = c.gravity_z;
+    const double h = (double)c.dt / (double)c.substeps;
+    d.h = (float)h;
+    d.hh = (float)(0.5 * h);
+    d.fault_eff_lo = c.fault_eff_lo; d.fault_eff_range = c.fault_eff_range;
+    d.dr_lo = c.dr_lo; d.dr_range = c.dr_range;
+    d.flicker_p = (c.pomdp_mode == OZL_POMDP_FLICKER_NOISE) ? 0.1f : c.pomdp_prob;      // POMDP.py:16-18
+    const float lo = (float)(1.0 - (double)c.noise_sigma), hi = (float)(1.0 + (double)c.noise_sigma);
+    d.noise_lo = lo;
+    d.noise_range = hi - lo;
+    d.pi_f = (float)M_PI;
+    d.sinc_c1 = (float)(-1.0 / 6.0); d.sinc_c2 = (float)(1.0 / 120.0);
+    d.cos_c1 = -0.5f; d.cos_c2 = (float)(1.0 / 24.0); d.cos_c3 = (float)(-1.0 / 720.0);
+}
+
+extern "C" int ozl_abi_version(void) { return OZL_ABI_VERSION; }
+extern "C" const char* ozl_last_error(void) { return g_err; }
+
+extern "C" int ozl_cfg_default(ozl_cfg* c, int64_t num_envs) {
+    if (!c) return set_error("ozl_cfg_default: cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->abi_version = OZL_ABI_VERSION;
+    c->num_envs = num_envs;
+    c->max_episode_length = 2000;
+    c->target_period = 500;
+    c->substeps = 2;
+    c->control_freq_inv = 1;
+    c->dt = 0.01f;
+    c->gravity_z = -9.81f;
+    c->clip_actions = 1.0f; c->clip_obs = 5.0f;
+    c->thrust_rate = (float)(0.01 * 2000); c->thrust_max = 2000.0f;
+    c->die_dist = 8.0f; c->die_z = 0.5f; c->up_coef = 5.0f;
+    const float sb[3] = {0.f, 0.f, 1.f}, sl[3] = {-1.5f, -1.5f, -0.2f};
+    const float sr[3] = {(float)(1.5 - (-1.5)), (float)(1.5 - (-1.5)), (float)(1.5 - (-0.2))};
+    const float ts[3] = {10.f, 10.f, 1.f}, to[3] = {-5.f, -5.f, 1.f};
+    for (int j = 0; j < 3; ++j) {
+        c->spawn_base[j] = sb[j]; c->spawn_lo[j] = sl[j]; c->spawn_range[j] = sr[j];
+        c->target_scale[j] = ts[j]; c->target_off[j] = to[j];
+    }
+    // composite x500 body, derived from assets/x500/x500.urdf (see ouzelum_b200/x500.py for the derivation)
+    const double m_b = 2.0, m_r = 0.016076923076923075, rz = 0.3, arm = 0.174;
+    const double ib[3] = {0.02166666666666667, 0.02166666666666667, 0.04000000000000001};
+    const double ir[3] = {3.8464910483993325e-07, 2.6115851691700804e-05, 2.649858234714004e-05};
+    const double M = m_b + 4.0 * m_r, cz = 4.0 * m_r * rz / M, dz = rz - cz, irxy = 0.5 * (ir[0] + ir[1]);
+    c->mass = (float)M;
+    c->com_z = (float)cz;
+    c->ixx = (float)(ib[0] + m_b * cz * cz + 4.0 * (irxy + m_r * (arm * arm + dz * dz)));
+    c->iyy = (float)(ib[1] + m_b * cz * cz + 4.0 * (irxy + m_r * (arm * arm + dz * dz)));
+    c->izz = (float)(ib[2] + 4.0 * (ir[2] + m_r * (2.0 * arm * arm)));
+    c->arm = (float)arm;
+    c->max_angvel = (float)(4.0 * M_PI);
+    c->fault_eff_lo = 0.0f; c->fault_eff_range = 0.5f;
+    c->dr_lo = 0.8f; c->dr_range = (float)(1.2 - 0.8);
+    c->collect_metrics = 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host: lifecycle
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
+    if (!cfg || !out) return set_error("ozl_create: NULL argument");
+    if (cfg->abi_version != OZL_ABI_VERSION)
+        return set_error("ozl_create: cfg.abi_version %d != library %d", cfg->abi_version, OZL_ABI_VERSION);
+    if (cfg->num_envs <= 0 || cfg->num_envs > 0x7FFFFFFFll) return set_error("ozl_create: num_envs out of range");
+    if (cfg->substeps <= 0 || cfg->control_freq_inv <= 0) return set_error("ozl_create: substeps/control_freq_inv must be > 0");
+    if (cfg->max_episode_length <= 1 || cfg->max_episode_length >= (1 << 29))
+        return set_error("ozl_create: max_episode_length out of range");
+    if (cfg->target_period <= 0) return set_error("ozl_create: target_period must be > 0");
+    if (cfg->pomdp_mode < 0 || cfg->pomdp_mode > 3) return set_error("ozl_create: unknown pomdp_mode %d", cfg->pomdp_mode);
+    if (!(cfg->mass > 0.f) || !(cfg->ixx > 0.f) || !(cfg->iyy > 0.f) || !(cfg->izz > 0.f))
+        return set_error("ozl_create: mass and inertia must be positive");
+    int ndev = 0;
+    if (check_cuda(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return 1;
+    if (device < 0 || device >= ndev) return set_error("ozl_create: device %d not available (%d visible)", device, ndev);
+    if (check_cuda(cudaSetDevice(device), "cudaSetDevice")) return 1;
+    cudaDeviceProp prop;
+    if (check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return 1;
+    if (prop.major != 10)
+        return set_error("ozl_create: this library is built for sm_100a (B200) only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    ozl_env* e = new ozl_env();
+    e->cfg = *cfg;
+    derive_dev_cfg(*cfg, e->dev);
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    const size_t n = (size_t)cfg->num_envs;
+    const size_t plane4 = align_up(n * sizeof(float4), 256), plane2 = align_up(n * sizeof(float2), 256);
+    const size_t ctrl = 256, metrics = align_up(sizeof(double) * kMetricSlots * kMetricStride, 256);
+    e->arena_bytes = 7 * plane4 + plane2 + ctrl + metrics;
+    if (check_cuda(cudaMalloc(&e->arena, e->arena_bytes), "cudaMalloc(state arena)")) { delete e; return 1; }
+    char* p = (char*)e->arena;
+    e->pl.d0 = (float4*)p; p += plane4;
+    e->pl.d1 = (float4*)p; p += plane4;
+    e->pl.d2 = (float4*)p; p += plane4;
+    e->pl.d3 = (float4*)p; p += plane4;
+    e->pl.s0 = (float4*)p; p += plane4;
+    e->pl.s1 = (float4*)p; p += plane4;
+    e->pl.s2 = (float4*)p; p += plane4;
+    e->pl.d4 = (float2*)p; p += plane2;
+    e->pl.ctrl = (unsigned long long*)p; p += ctrl;
+    e->pl.metrics = (double*)p;
+    *out = e;
+    return ozl_reset_all(e, cfg->seed, nullptr);
+}
+
+extern "C" int ozl_destroy(ozl_env* env) {
+    if (!env) return 0;
+    cudaSetDevice(env->device);
+    cudaFree(env->arena);
+    delete env;
+    return 0;
+}
+
+static inline unsigned blocks_for(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+#define OZL_ENV_CHECK(name)                                        \
+    if (!env) return set_error(name ": env is NULL");              \
+    cudaStream_t st = (cudaStream_t)stream;
+
+extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
+    OZL_ENV_CHECK("ozl_reset_all");
+    env->cfg.seed = seed;
+    env->dev.seed = seed;
+    int64_t n = env->cfg.num_envs;
+    if (n < kMetricSlots * kMetricStride) n = kMetricSlots * kMetricStride;
+    init_state_kernel<<<blocks_for(n, 256), 256, 0, st>>>(env->dev, env->pl);
+    return check_cuda(cudaGetLastError(), "init_state_kernel");
+}
+
+// Block size: 128 threads keeps >= 1 block on every SM down to ~19k envs and lets 16k-env launches use 128 SMs.
+constexpr int kStepBlock = 128;
+
+extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
+                        uint8_t* timeout, float* ep_ret, void* stream) {
+    OZL_ENV_CHECK("ozl_step");
+    if (!actions || !obs || !rew || !reset || !progress) return set_error("ozl_step: NULL buffer");
+    if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("ozl_step: actions/obs must be 16-byte aligned");
+    quad_step_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
+        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret);
+    return check_cuda(cudaGetLastError(), "quad_step_kernel");
+}
+
+extern "C" int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int64_t* reset, int64_t* progress, void* stream) {
+    OZL_ENV_CHECK("ozl_rollout");
+    if (K <= 0) return set_error("ozl_rollout: K must be > 0");
+    if (!obs || !rew || !reset || !progress) return set_error("ozl_rollout: NULL buffer");
+    quad_rollout_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
+        env->dev, env->pl, K, obs, rew, reset, progress);
+    return check_cuda(cudaGetLastError(), "quad_rollout_kernel");
+}
+
+extern "C" int ozl_get_state(ozl_env* env, float* root13, float* thrust4, float* target3, float* ep_ret, void* stream) {
+    OZL_ENV_CHECK("ozl_get_state");
+    get_state_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, root13, thrust4, target3, ep_ret);
+    return check_cuda(cudaGetLastError(), "get_state_kernel");
+}
+extern "C" int ozl_set_state(ozl_env* env, const float* root13, const float* thrust4, const float* target3,
+                             const float* ep_ret, void* stream) {
+    OZL_ENV_CHECK("ozl_set_state");
+    set_state_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, root13, thrust4, target3, ep_ret);
+    return check_cuda(cudaGetLastError(), "set_state_kernel");
+}
+extern "C" int ozl_get_params(ozl_env* env, float* params7, int32_t* fault2, void* stream) {
+    OZL_ENV_CHECK("ozl_get_params");
+    get_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params7, fault2);
+    return check_cuda(cudaGetLastError(), "get_params_kernel");
+}
+extern "C" int ozl_set_params(ozl_env* env, const float* params7, const int32_t* fault2, void* stream) {
+    OZL_ENV_CHECK("ozl_set_params");
+    set_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params7, fault2);
+    return check_cuda(cudaGetLastError(), "set_params_kernel");
+}
+
+extern "C" int ozl_get_step_count(ozl_env* env, uint64_t* out, void* stream) {
+    OZL_ENV_CHECK("ozl_get_step_count");
+    if (!out) return set_error("ozl_get_step_count: out is NULL");
+    unsigned long long v = 0;
+    if (check_cuda(cudaMemcpyAsync(&v, env->pl.ctrl, sizeof(v), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) return 1;
+    if (check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return 1;
+    *out = v;
+    return 0;
+}
+extern "C" int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream) {
+    OZL_ENV_CHECK("ozl_set_step_count");
+    set_step_kernel<<<1, 1, 0, st>>>(env->pl, (unsigned long long)value);
+    return check_cuda(cudaGetLastError(), "set_step_kernel");
+}
+
+extern "C" int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream) {
+    OZL_ENV_CHECK("ozl_metrics_read");
+    if (!out16) return set_error("ozl_metrics_read: out16 is NULL");
+    metrics_read_kernel<<<1, 32, 0, st>>>(env->pl, out16, clear);
+    return check_cuda(cudaGetLastError(), "metrics_read_kernel");
+}
