@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the x500 rotor-fault env-step path (BASELINE.json metric: env-steps/s, whole box).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                         the reference-structured CPU path (oracle port)
+
+One "step" = one pass of the fused step kernel over every env of every rank, actions read from HBM,
+obs / reward / reset / progress written to HBM (SURVEY 8d "mode A").  Workload = BASELINE configs[1]:
+x500 tracking with a single-rotor loss-of-effectiveness fault, 16384 envs per GPU (weak scaling).
+
+Timing: W warm-up steps, then EXACTLY K timed steps.  The per-GPU working set at this workload (4.9 MB)
+is far below the 126 MB L2, so L2 is flushed (a 256 MiB buffer is overwritten) before every timed step and
+each step is timed by its own CUDA-event pair on the launching stream; the reported time is the sum of the
+K step times, max over ranks.  The roofline object is measured live on the same kernel at 1 Mi envs (311 MB
+per launch > L2, so no flush is needed there) -- both are labelled.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_ENV_STEP = 284          # reads 144 + writes 140
+WORKLOAD = "x500 trajectory tracking + single-rotor loss-of-effectiveness fault, 16384 envs per GPU (BASELINE configs[1])"
+METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=1000)
+    p.add_argument("--warmup", type=int, default=100)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--envs", type=int, default=16384, help="envs per GPU")
+    p.add_argument("--roofline-envs", type=int, default=1 << 20)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--roofline-only", action="store_true", help="profiling aid: run only the 1 Mi-env roofline region")
+    return p.parse_args()
+
+
+def task_cfg_kwargs():
+    """configs[1]: Ouzelum + rotor fault (rotor = Philox & 3, onset ~ U{0..1999}, effectiveness ~ U(0, 0.5))."""
+    return dict(fault_mode=1, fault_eff_lo=0.0, fault_eff_range=0.5, collect_metrics=1)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while a timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.ok:
+            self.th.start()
+
+    def region(self, on):
+        (self._active.set if on else self._active.clear)()
+
+    def result(self):
+        self._stop.set()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": sorted(self.reasons),
+                    "note": "no NVML samples inside the timed region"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(n_envs, budget_s, seed, max_steps=None):
+    """Times the oracle port of the reference step (torch-CPU eager, all host threads) on a bounded sample.
+    Returns (env-steps/s, steps run, envs per step, threads)."""
+    import torch
+    from oracle.quad_step import QuadStepOracle, default_cfg
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = default_cfg(n_envs, seed=seed, **{k: v for k, v in task_cfg_kwargs().items() if k != "collect_metrics"})
+    ora = QuadStepOracle(cfg)
+    g = torch.Generator().manual_seed(seed)
+    acts = [torch.rand(n_envs, 4, generator=g) * 2 - 1 for _ in range(4)]
+    for k in range(2):
+        ora.step(acts[k])                       # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    ora.step(acts[2])
+    per = max(time.perf_counter() - t0, 1e-4)
+    steps = max(3, int(budget_s / per))
+    if max_steps:
+        steps = min(steps, max_steps)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ora.step(acts[k & 3])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, steps, n_envs, threads
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own step cannot run here or on the GPU box (Isaac Gym / PhysX is a closed
+    binary that is not in the reference tree), so the arm times the oracle PORT of it -- the same
+    torch-eager op sequence on the host cores -- on our arm's workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.envs
+    # bound the run: K+W steps of the full workload if that fits ~2 minutes, else a smaller env sample per step
+    import torch
+    from oracle.quad_step import QuadStepOracle, default_cfg
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+
+    def mk(m):
+        return QuadStepOracle(default_cfg(m, seed=args.seed, **{k: v for k, v in task_cfg_kwargs().items() if k != "collect_metrics"}))
+    probe = mk(n)
+    a = torch.rand(n, 4) * 2 - 1
+    probe.step(a)
+    t0 = time.perf_counter()
+    probe.step(a)
+    per = time.perf_counter() - t0
+    total = per * (args.steps + args.warmup)
+    sample = n
+    if total > 120.0:
+        sample = max(256, int(n * 120.0 / total) // 256 * 256)
+    ora = mk(sample)
+    g = torch.Generator().manual_seed(args.seed)
+    acts = [torch.rand(sample, 4, generator=g) * 2 - 1 for _ in range(4)]
+    for k in range(args.warmup):
+        ora.step(acts[k & 3])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ora.step(acts[k & 3])
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_step": sample,
+                   "note": "CPU restatement of the reference step (PhysX unavailable): oracle port, torch-CPU eager"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {sample} envs of the workload (host cores only)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ouzelum_b200
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = _lib.default_cfg(n, seed=args.seed, env_id_base=rank * n, **task_cfg_kwargs())
+    sim = QuadSim(cfg, dev)
+    obs = torch.zeros(n, 13, device=dev)
+    rew = torch.zeros(n, device=dev)
+    reset = torch.ones(n, dtype=torch.int64, device=dev)
+    prog = torch.zeros(n, dtype=torch.int64, device=dev)
+    tout = torch.zeros(n, dtype=torch.uint8, device=dev)
+    epr = torch.zeros(n, device=dev)
+    g = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    pool = [torch.rand(n, 4, device=dev, generator=g) * 2 - 1 for _ in range(8)]   # synthetic actions, resident in HBM
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                  # > 126 MB L2
+    metrics_dev = torch.zeros(16, dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def step(k):
+        sim.step(pool[k & 7], obs, rew, reset, prog, tout, epr)
+
+    def metrics_allreduce():
+        # config 4: the ONLY collective on the path -- a 16-double metrics vector, every 16 steps, off the step stream
+        sim.metrics(clear=False, out=metrics_dev)
+        if world > 1:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_reduce(metrics_dev, op=dist.ReduceOp.SUM)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    if args.roofline_only:
+        K, W = 1, 1
+        args.no_e2e = args.no_cpu_baseline = True
+
+    # ---- headline: K steps, L2 flushed before each, per-step CUDA events -----------------------------------------
+    for k in range(W):
+        step(k)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    clocks.region(True)
+    for k in range(K):
+        flush.zero_()
+        ev[k][0].record()
+        step(k)
+        ev[k][1].record()
+        if (k & 15) == 15:
+            metrics_allreduce()
+    barrier()
+    clocks.region(False)
+    ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * K / (ms * 1e-3)
+
+    # ---- warm-L2 variant (what a resident 16k-env rollout actually sees): CUDA graph of back-to-back steps ---------
+    chunk = K if K <= 500 else 500
+    gr = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(gr):
+        for k in range(chunk):
+            step(k)
+    reps, rem = K // chunk, K % chunk
+    gr.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.region(True)
+    e0.record()
+    for _ in range(reps):
+        gr.replay()
+    for k in range(rem):
+        step(k)
+    e1.record()
+    barrier()
+    clocks.region(False)
+    tw = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    warm_ms = float(tw.item())
+    value_warm = world * n * K / (warm_ms * 1e-3)
+
+    # ---- e2e through the public API (make -> VecTask.step) with HOST buffers ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        tc = ouzelum_b200.task_config("Ouzelum", n, rotorFault={"enable": True}, seed=args.seed, envIdBase=rank * n)
+        env = ouzelum_b200.make(seed=args.seed, task="Ouzelum", num_envs=n, sim_device=str(dev), rl_device=str(dev),
+                                headless=True, cfg=tc)
+        env.reset()
+        h_act = [(torch.rand(n, 4) * 2 - 1).pin_memory() for _ in range(4)]
+        d_act = torch.empty(n, 4, device=dev)
+        h_obs = torch.empty(n, 13).pin_memory()
+        h_rew = torch.empty(n).pin_memory()
+        h_rst = torch.empty(n, dtype=torch.int64).pin_memory()
+
+        def e2e_step(k):
+            d_act.copy_(h_act[k & 3], non_blocking=True)
+            o, r, d, _ = env.step(d_act)
+            h_obs.copy_(o["obs"], non_blocking=True)
+            h_rew.copy_(r, non_blocking=True)
+            h_rst.copy_(d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the host consumes the result before the next action
+
+        for k in range(W):
+            e2e_step(k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(K):
+            e2e_step(k)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * K / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": world * h_act[0].numel() * 4,
+               "d2h_bytes_per_step": world * (h_obs.numel() * 4 + h_rew.numel() * 4 + h_rst.numel() * 8),
+               "api": "ouzelum_b200.make(...).step(actions): pinned host -> device, fused step, device -> pinned host, sync"}
+        env.close()
+
+    # ---- roofline of the dominant (only) kernel, live, at an L2-exceeding size ------------------------------------
+    roofline = roofline_wl = None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    if rank == 0:
+        nb = args.roofline_envs
+        del flush
+        cfgb = _lib.default_cfg(nb, seed=args.seed, **task_cfg_kwargs())
+        simb = QuadSim(cfgb, dev)
+        ob, rb = torch.zeros(nb, 13, device=dev), torch.zeros(nb, device=dev)
+        rsb, pb = torch.ones(nb, dtype=torch.int64, device=dev), torch.zeros(nb, dtype=torch.int64, device=dev)
+        tb, eb = torch.zeros(nb, dtype=torch.uint8, device=dev), torch.zeros(nb, device=dev)
+        ab = [torch.rand(nb, 4, device=dev) * 2 - 1 for _ in range(2)]
+        for k in range(10):
+            simb.step(ab[k & 1], ob, rb, rsb, pb, tb, eb)
+        torch.cuda.synchronize()
+        reps_b = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.region(True)
+        e0.record()
+        for k in range(reps_b):
+            simb.step(ab[k & 1], ob, rb, rsb, pb, tb, eb)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks.region(False)
+        per_launch_s = e0.elapsed_time(e1) * 1e-3 / reps_b
+        ach = ALG_BYTES_PER_ENV_STEP * nb / per_launch_s / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                    "kernel": "quad_step_kernel<128>", "n_envs": nb, "launch_us": per_launch_s * 1e6,
+                    "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "peak_source": peak_src,
+                    "l2": "inputs (311 MB/launch) exceed the 126 MB L2; no flush",
+                    "env_steps_per_sec_at_this_size": nb / per_launch_s}
+        ach_wl = ALG_BYTES_PER_ENV_STEP * n / (ms * 1e-3 / K) / 1e9
+        roofline_wl = {"bound": "launch/latency (4.9 MB per launch, one partial wave)", "achieved": ach_wl, "peak": peak,
+                       "unit": "GB/s", "frac": ach_wl / peak, "n_envs": n, "launch_us": ms * 1e3 / K}
+        del simb
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, steps_c, envs_c, threads = cpu_port_rate(n, budget_s=12.0, seed=args.seed)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{steps_c} steps x {envs_c} envs (oracle port of the reference step, torch-CPU eager; PhysX unavailable)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs_total": world * n, "mode": "A: actions read from HBM, obs/rew/reset/progress written to HBM",
+                       "l2": "flushed (256 MiB overwritten) before every timed step; per-step CUDA events",
+                       "parallelism": f"env-sharded x{world}, no per-step collective; 16-double metrics all-reduce every 16 steps"},
+            "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms / K,
+            "clocks": clocks.result(),
+            "e2e": e2e, "gpu_launches": K,
+            "roofline": roofline, "roofline_at_workload": roofline_wl,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+"""`Ouzelum`: x500 quadcopter tracking a randomly re-sampled waypoint, as ONE fused kernel per step.
+
+Mirror of isaacgymenvs/tasks/ouzelum.py (class surface :40-99, hooks :180-295, reward :302-332).
+The reference builds an Isaac Gym sim with an O(N) Python loop (:153-168) and steps it with ~45
+eager launches + 3 host syncs + PhysX; here `create_sim` allocates the SoA state through the C ABI
+and `step` is a single `ozl_step` launch with no host synchronisation.
+"""
+import math
+
+import torch
+
+from .. import _lib
+from ..sim import QuadSim
+from ..vec_task import VecTask
+
+_POMDP = {"none": 0, None: 0, "flicker": 1, "random_noise": 2, "flickering_and_random_noise": 3}
+
+
+def x500_cfg_from_task(cfg, num_envs, **over):
+    """Translate the reference-style nested task dict into the C `ozl_cfg`."""
+    env, sim = cfg["env"], cfg.get("sim", {})
+    dt = float(sim.get("dt", 0.01))
+    fault = env.get("rotorFault", {}) or {}
+    dr = env.get("domainRandomization", {}) or {}
+    pomdp = env.get("POMDP", "none")
+    if pomdp not in _POMDP:
+        # isaacgymenvs/utils/POMDP.py:19-20
+        raise ValueError("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!")
+    kw = dict(
+        env_id_base=int(env.get("envIdBase", 0)), seed=int(env.get("seed", 0)),
+        max_episode_length=int(env["maxEpisodeLength"]),
+        substeps=int(sim.get("substeps", 2)), control_freq_inv=int(env.get("controlFrequencyInv", 1)),
+        dt=dt, gravity_z=float(sim.get("gravity", [0, 0, -9.81])[2]),
+        clip_actions=float(min(env.get("clipActions", math.inf), 3.0e38)),
+        clip_obs=float(min(env.get("clipObservations", math.inf), 3.0e38)),
+        thrust_rate=dt * 2000,                         # ouzelum.py:237-238
+        lin_drag=float(env.get("linDrag", 0.0)), yaw_km=float(env.get("yawKm", 0.0)),
+        fault_mode=1 if fault.get("enable", False) else 0,
+        fault_eff_lo=float(fault.get("effLow", 0.0)),
+        fault_eff_range=float(fault.get("effHigh", 0.5)) - float(fault.get("effLow", 0.0)),
+        dr_enable=1 if dr.get("enable", False) else 0,
+        dr_lo=float(dr.get("low", 0.8)), dr_range=float(dr.get("high", 1.2)) - float(dr.get("low", 0.8)),
+        pomdp_mode=_POMDP[pomdp], pomdp_prob=float(env.get("pomdp_prob", 0.0)),
+        noise_sigma=float(env.get("pomdp_prob", 0.0)),  # POMDP.py:8-9: one knob feeds both
+        collect_metrics=1 if env.get("collectMetrics", True) else 0,
+    )
+    kw.update(over)
+    return _lib.default_cfg(num_envs, **kw)
+
+
+class X500Task(VecTask):
+    """Shared machinery of the x500 tasks: owns the `QuadSim` handle and launches the fused step."""
+
+    num_x500_obs = 13
+    num_x500_actions = 4
+
+    def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless,
+                 virtual_screen_capture=False, force_render=False):
+        self.cfg = cfg
+        self.max_episode_length = self.cfg["env"]["maxEpisodeLength"]
+        self.debug_viz = self.cfg["env"].get("enableDebugVis", False)
+        self.cfg["env"]["numObservations"] = self.num_x500_obs     # ouzelum.py:50
+        self.cfg["env"]["numActions"] = self.num_x500_actions      # ouzelum.py:55
+        super().__init__(config=self.cfg, rl_device=rl_device, sim_device=sim_device,
+                         graphics_device_id=graphics_device_id, headless=headless,
+                         virtual_screen_capture=virtual_screen_capture, force_render=force_render)
+        self.dt = float(self.cfg.get("sim", {}).get("dt", 0.01))
+        self._timeout_u8 = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        self.timeout_buf = self._timeout_u8.view(torch.bool)
+        # RecordEpisodeStatisticsTorch "r"/"l" equivalents (RPO-LSTM/utils.py:24-30), filled by the kernel
+        self.episode_return_buf = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._static_actions = None
+        self.use_cuda_graph = bool(self.cfg["env"].get("useCudaGraph", False))
+
+    # ---- overridable pieces --------------------------------------------------------------------------
+    def _native_cfg(self):
+        return x500_cfg_from_task(self.cfg, self.num_envs)
+
+    def create_sim(self):
+        self.native_cfg = self._native_cfg()
+        self.sim = QuadSim(self.native_cfg, self.device)
+
+    # ---- fused step ------------------------------------------------------------------------------------
+    def _launch(self, actions):
+        self.sim.step(actions, self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf,
+                      self._timeout_u8, self.episode_return_buf)
+
+    def _fused_step(self, actions):
+        if not self.use_cuda_graph:
+            self._launch(actions)
+            return
+        if self._graph is None:
+            self._static_actions = torch.empty_like(actions)
+            self._static_actions.copy_(actions)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(self._static_actions)
+            self._graph = g
+        self._static_actions.copy_(actions)
+        self._graph.replay()
+
+    # ---- reference-style state views (copies out of the private SoA state) ------------------------------
+    @property
+    def root_states(self):
+        return self.sim.get_state()["root"]
+
+    @property
+    def root_positions(self):
+        return self.root_states[:, 0:3]
+
+    @property
+    def root_quats(self):
+        return self.root_states[:, 3:7]
+
+    @property
+    def root_linvels(self):
+        return self.root_states[:, 7:10]
+
+    @property
+    def root_angvels(self):
+        return self.root_states[:, 10:13]
+
+    @property
+    def thrusts(self):
+        return self.sim.get_state()["thrust"]
+
+    @property
+    def target_root_positions(self):
+        return self.sim.get_state()["target"]
+
+    def set_root_states(self, root):
+        self.sim.set_state(root=root)
+
+    def reset_idx(self, env_ids):
+        """ouzelum.py:192-216.  The re-initialisation itself happens inside the next step's kernel (exactly when
+        the reference's takes effect: pre_physics_step, ouzelum.py:226-229); here the request is recorded."""
+        self.reset_buf[env_ids] = 1
+
+    def metrics(self, clear=False):
+        """Episode / reward metrics vector accumulated in-kernel (see include/ouzelum_b200.h)."""
+        return self.sim.metrics(clear=clear)
+
+    def close(self):
+        self.sim.close()
+
+
+class Ouzelum(X500Task):
+    """isaacgymenvs/tasks/ouzelum.py: target re-sampled in a 10x10x1 box every 500 steps, die z<0.5 or dist>8."""
