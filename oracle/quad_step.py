@@ -112,13 +112,21 @@ def compute_ingenuity_reward(root_positions, target_root_positions, root_quats, 
     return reward, reset
 
 
+def div_by_scalar(x, s):
+    """`tensor / python_scalar` with torch-CUDA semantics: aten/native/cuda/BinaryDivTrueKernel.cu multiplies by the
+    reciprocal computed in the tensor's dtype ("may lose one bit of precision compared to computing the division");
+    torch-CPU divides.  The reference runs on CUDA, so the oracle follows the CUDA evaluation (<= 1 ulp apart)."""
+    one = torch.ones((), dtype=x.dtype)
+    return x * (one / torch.tensor(float(s), dtype=x.dtype))
+
+
 def compute_observations(root_states, target_root_positions):
     """isaacgymenvs/tasks/ouzelum.py:280-285."""
     obs = torch.empty(root_states.shape[0], 13, dtype=root_states.dtype)
-    obs[..., 0:3] = (target_root_positions - root_states[:, 0:3]) / 3
+    obs[..., 0:3] = div_by_scalar(target_root_positions - root_states[:, 0:3], 3)
     obs[..., 3:7] = root_states[:, 3:7]
-    obs[..., 7:10] = root_states[:, 7:10] / 2
-    obs[..., 10:13] = root_states[:, 10:13] / math.pi
+    obs[..., 7:10] = div_by_scalar(root_states[:, 7:10], 2)
+    obs[..., 10:13] = div_by_scalar(root_states[:, 10:13], math.pi)
     return obs
 
 

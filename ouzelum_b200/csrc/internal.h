@@ -17,7 +17,7 @@ constexpr int kMetricStride = 32;      // doubles per slot (16 used)
 // and a warp touches 512 contiguous bytes per plane.
 //   dynamic (read+written every step):  d0 {px,py,pz,qx} d1 {qy,qz,qw,vx} d2 {vy,vz,wx,wy} d3 {wz,T0,T1,T2} d4 {T3,ep_ret}
 //   static  (read every step, written only on reset/resample):
-//           s0 {tx,ty,tz,fault_eff} s1 {mass,ixx,iyy,izz} s2 {arm,thrust_scale,fault_word,spare}
+//           s0 {tx,ty,tz,fault_eff} s1 {1/mass,ixx,iyy,izz} s2 {arm,thrust_scale,fault_word,mass}
 struct Planes {
     float4 *d0, *d1, *d2, *d3;
     float2* d4;

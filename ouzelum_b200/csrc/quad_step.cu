@@ -36,8 +36,8 @@ __device__ __forceinline__ void unpack(const Loaded& L, Env& e) {
     e.T[0] = L.d3.y; e.T[1] = L.d3.z; e.T[2] = L.d3.w; e.T[3] = L.d4.x;
     e.ep_ret = L.d4.y;
     e.tgt[0] = L.s0.x; e.tgt[1] = L.s0.y; e.tgt[2] = L.s0.z; e.eff = L.s0.w;
-    e.mass = L.s1.x; e.ixx = L.s1.y; e.iyy = L.s1.z; e.izz = L.s1.w;
-    e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z);
+    e.inv_m = L.s1.x; e.ixx = L.s1.y; e.iyy = L.s1.z; e.izz = L.s1.w;
+    e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z); e.mass = L.s2.w;
 }
 __device__ __forceinline__ void load_env(const Planes& pl, int64_t i, Loaded& L) {
     L.d0 = pl.d0[i]; L.d1 = pl.d1[i]; L.d2 = pl.d2[i]; L.d3 = pl.d3[i]; L.d4 = pl.d4[i];
@@ -52,8 +52,8 @@ __device__ __forceinline__ void store_dynamic(const Planes& pl, int64_t i, const
 }
 __device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const Env& e) {
     pl.s0[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
-    pl.s1[i] = make_float4(e.mass, e.ixx, e.iyy, e.izz);
-    pl.s2[i] = make_float4(e.arm, e.ks, __uint_as_float(e.fault), 0.0f);
+    pl.s1[i] = make_float4(e.inv_m, e.ixx, e.iyy, e.izz);
+    pl.s2[i] = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
 }
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
@@ -61,6 +61,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+
+// TMA 1-D bulk copy shared -> global (SASS: UBLKCP).  Used to write the block's contiguous [BLOCK,13] observation
+// tile with one instruction instead of a per-thread copy loop.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -112,8 +122,17 @@ __device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl
 }
 
 // ------------------------------------------------------------------------------------------------ K1
+#ifndef OZL_OBS_BULK
+#define OZL_OBS_BULK 1
+#endif
+#ifndef OZL_STEP_BLOCK
+#define OZL_STEP_BLOCK 128
+#endif
+#ifndef OZL_STEP_MINB
+#define OZL_STEP_MINB 8
+#endif
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
 quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out) {
@@ -140,8 +159,14 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         unpack(L, e);
         const float act[4] = {a4.x, a4.y, a4.z, a4.w};
         const uint32_t genv = c.env_id_base + (uint32_t)i;
+#ifdef OZL_EXPERIMENT_NO_COMPUTE   // memory-system ceiling experiment only (never shipped)
+        for (int j = 0; j < 3; ++j) { e.p[j] += act[j] + e.tgt[j] + e.inv_m; e.v[j] += e.ixx + e.arm; o.obs[j] = e.p[j]; o.obs[3 + j] = e.v[j]; o.obs[6 + j] = e.w[j]; o.obs[9 + j] = e.q[j]; }
+        o.obs[12] = e.T[3] + e.eff + e.mass + __uint_as_float(e.fault);
+        o.rew = e.ep_ret; o.prog = prog + 1; o.reset = rst;
+#else
         env_step(e, act, prog, rst, genv, step, c, o);
         obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
+#endif
 
         store_dynamic(pl, i, e);
         if (o.static_dirty) store_static(pl, i, e);
@@ -153,6 +178,9 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
 #pragma unroll
         for (int j = 0; j < 13; ++j) s_obs[threadIdx.x * 13 + j] = o.obs[j];   // stride 13: conflict-free
     }
+#if OZL_OBS_BULK
+    fence_proxy_async_smem();          // make the generic-proxy smem writes visible to the bulk-copy (async) proxy
+#endif
     __syncthreads();
     // [N,13] row-major observation tile of this block is contiguous: write it with full 16-byte lanes
     {
@@ -161,14 +189,25 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         float* dst = obs + base * 13;
         const int nflt = n_here * 13;
         if ((nflt & 3) == 0) {   // base*13*4 bytes is 16-byte aligned whenever BLOCK % 4 == 0
+#if OZL_OBS_BULK
+            if (threadIdx.x == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
+#else
             float4* d4p = reinterpret_cast<float4*>(dst);
             const float4* s4 = reinterpret_cast<const float4*>(s_obs);
-            for (int k = threadIdx.x; k < nflt / 4; k += BLOCK) d4p[k] = s4[k];
+#pragma unroll
+            for (int it = 0; it < (BLOCK * 13 / 4 + BLOCK - 1) / BLOCK; ++it) {
+                const int k = threadIdx.x + it * BLOCK;
+                if (k < nflt / 4) d4p[k] = s4[k];
+            }
+#endif
         } else {
             for (int k = threadIdx.x; k < nflt; k += BLOCK) dst[k] = s_obs[k];
         }
     }
     block_epilogue<BLOCK>(c, pl, valid, o, step, 1u, s_m);
+#if OZL_OBS_BULK
+    if (threadIdx.x == 0) bulk_wait_read_all();   // s_obs must stay alive until the bulk copy has read it
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ mode B
@@ -309,7 +348,7 @@ __global__ void set_params_kernel(const Planes pl, int64_t n, const float* param
     unpack(L, e);
     if (params7) {
         const float* p = params7 + i * 7;
-        e.mass = p[0]; e.ixx = p[1]; e.iyy = p[2]; e.izz = p[3]; e.arm = p[4]; e.ks = p[5]; e.eff = p[6];
+        e.mass = p[0]; e.inv_m = 1.0f / p[0]; e.ixx = p[1]; e.iyy = p[2]; e.izz = p[3]; e.arm = p[4]; e.ks = p[5]; e.eff = p[6];
     }
     if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | ((uint32_t)fault2[i * 2 + 1] << 2);
     store_static(pl, i, e);
@@ -328,7 +367,7 @@ __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     e.ep_ret = 0.0f;
     e.tgt[0] = 0.0f; e.tgt[1] = 0.0f; e.tgt[2] = 1.0f;        // ouzelum.py:71-73
     e.eff = 1.0f;
-    e.mass = c.mass; e.ixx = c.ixx; e.iyy = c.iyy; e.izz = c.izz; e.arm = c.arm; e.ks = 1.0f;
+    e.mass = c.mass; e.inv_m = 1.0f / c.mass; e.ixx = c.ixx; e.iyy = c.iyy; e.izz = c.izz; e.arm = c.arm; e.ks = 1.0f;
     e.fault = FAULT_NEVER << 2;
     store_dynamic(pl, i, e);
     store_static(pl, i, e);
@@ -385,7 +424,16 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
     const float lo = (float)(1.0 - (double)c.noise_sigma), hi = (float)(1.0 + (double)c.noise_sigma);
     d.noise_lo = lo;
     d.noise_range = hi - lo;
-    d.pi_f = (float)M_PI;
+    d.inv3 = 1.0f / 3.0f;
+    d.half = 1.0f / 2.0f;
+    d.inv_pi = 1.0f / (float)M_PI;
+    {   // n % d == n - ((n * magic) >> shift) * d for all 0 <= n < 2^31  (magic = ceil(2^(31+l) / d), l = ceil(log2 d))
+        const uint32_t dd = (uint32_t)c.target_period;
+        uint32_t l = 0;
+        while ((1ull << l) < dd) ++l;
+        d.period_shift = 31 + l;
+        d.period_magic = (uint32_t)(((1ull << (31 + l)) + dd - 1) / dd);
+    }
     d.sinc_c1 = (float)(-1.0 / 6.0); d.sinc_c2 = (float)(1.0 / 120.0);
     d.cos_c1 = -0.5f; d.cos_c2 = (float)(1.0 / 24.0); d.cos_c3 = (float)(-1.0 / 720.0);
 }
@@ -505,7 +553,7 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 }
 
 // Block size: 128 threads keeps >= 1 block on every SM down to ~19k envs and lets 16k-env launches use 128 SMs.
-constexpr int kStepBlock = 128;
+constexpr int kStepBlock = OZL_STEP_BLOCK;
 
 extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
                         uint8_t* timeout, float* ep_ret, void* stream) {
