@@ -129,6 +129,70 @@ int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream);
  * Replaces RecordEpisodeStatisticsTorch + the trainer's Python scan (RPO-LSTM/utils.py:20-35, main.py:105-113). */
 int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Companion kernels.  All buffers are caller-owned device memory; `n` = number of envs.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Lee geometric controllers.  Replaces Controller.__call__ (isaacgymenvs/controllers/controller.py:45-48) and
+ * LeePositionController / LeeVelocityController / LeeAttitudeContoller.__call__
+ * (controllers/position_control.py:19-109, velocity_control.py:17-112, attitude_control.py:17-78).
+ *   mode 0 position, 1 velocity, 2 attitude (anything else: error "Invalid controller name", controller.py:34)
+ *   state13 [n,13] f32 (pos, quat xyzw, linvel, angvel world), cmd4 [n,4] f32 (16-byte aligned)
+ *   gains16  HOST pointer: kP[3], kV[3], kR[3], kOmega[3], scale_input[4]   (controllers/control_config.py:13-18)
+ *   thrust [n] f32, torque3 [n,3] f32 ("m*g normalised thrust and inertia normalised torques") */
+int ozl_lee_control(int32_t mode, int64_t n, const float* state13, const float* cmd4, const float* gains16,
+                    float* thrust, float* torque3, void* stream);
+
+/* Position/velocity/accel-bias Kalman filter bank.  State planes are SoA: x9xN = [9][n] f32, P81xN = [81][n] f32
+ * (row-major 9x9 per env, full matrix -- the reference's (I-KH)P update is not symmetric in float32).
+ * Replaces PVFilter.__init__ / prediction_step / correction_step (isaacgymenvs/PVFilter.py:7-110) and the per-env
+ * Python loop around them (tasks/ekf_lee_landed.py:417-444). */
+typedef struct ozl_pv_args {
+    int64_t n;
+    float* x9xN;
+    float* P81xN;
+    const float* accel3;      /* [n,3] body-frame specific force (prediction input)                    */
+    const float* quat4;       /* [n,4] orientation, 16-byte aligned; xyzw if flip_qw else wxyz         */
+    const float* pos_meas3;   /* [n,3] or NULL: position fix candidates                                */
+    const float* vel_meas3;   /* [n,3] or NULL: velocity fix candidates                                */
+    const uint8_t* pos_mask;  /* [n] or NULL: which envs take the position fix; NULL => trigger rule   */
+    const uint8_t* vel_mask;  /* [n] or NULL                                                           */
+    float dt;
+    float acc_var[3];         /* process accel variance                                                */
+    float pos_var[3];         /* used only if pos_var_given                                            */
+    float vel_var[3];         /* used only if vel_var_given (the reference passes gps_var=None => R = 0, PVFilter.py:76-79) */
+    int32_t pos_var_given, vel_var_given;
+    int32_t flip_qw;          /* PVFilter.py:32-35                                                     */
+    int32_t do_predict;       /* 0: corrections only                                                   */
+    /* trigger rule when a mask is NULL: fix iff ((iter_base + env) % period) == phase; period 0 = never.
+     * Reference (tasks/ekf_lee_landed.py:153-154,425-440, counters shared by all envs): position (7,6), velocity (3,0)
+     * with iter_base = step * num_envs. */
+    uint32_t pos_period, pos_phase, vel_period, vel_phase;
+    uint64_t iter_base;
+} ozl_pv_args;
+int ozl_pv_init(int64_t n, float* x9xN, float* P81xN, void* stream);                       /* x = 0, P = 1000 I  (PVFilter.py:11-12) */
+int ozl_pv_reset(int64_t n, float* x9xN, const int64_t* flags, const float* root13, void* stream);   /* x[flagged] = [pos, vel, 0]  (ekf_lee_landed.py:353-358); flags NULL = all */
+int ozl_pv_step(const ozl_pv_args* args, void* stream);                                    /* predict, then gated position fix, then gated velocity fix: one launch */
+
+/* Attitude EKF bank (float64).  q4xN = [4][n] f64 wxyz, P16xN = [16][n] f64.  Replaces EKF.__init__ / EKF.update
+ * (isaacgymenvs/ahrs_ekf.py:982-1012, 1280-1337, `ang` branch) and the loop at tasks/ekf_lee_landed.py:378-391.
+ * The a-priori quaternion is normalised inside (the reference's caller does q/|q|, ekf_lee_landed.py:386). */
+int ozl_ekf_init(int64_t n, double* q4xN, double* P16xN, void* stream);                    /* q = (1,0,0,0), P = I4 (ahrs_ekf.py:995) */
+int ozl_ekf_set_q(int64_t n, double* q4xN, const float* quat_xyzw, const int64_t* flags, void* stream);   /* Q_state[flagged] = quat[[3,0,1,2]]; flags NULL = all */
+int ozl_ekf_update(int64_t n, double* q4xN, double* P16xN, const float* gyr3, const float* ang4, int32_t ang_xyzw,
+                   double Dt, double g_noise, void* stream);
+
+/* Sensor-fault model on an [n,d] f32 array.  Replaces POMDPWrapper.observation (isaacgymenvs/utils/POMDP.py:23-42).
+ * mode: OZL_POMDP_FLICKER / _NOISE / _FLICKER_NOISE (anything else: the reference's ValueError text).
+ * Draws are counter-based: (seed, global env id, step, stream_id) -- stream_id separates several uses in one step. */
+int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step,
+                          int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream);
+
+/* RecordEpisodeStatisticsTorch.step (isaacgymenvs/RPO-LSTM/utils.py:20-35) in one launch:
+ * ep_ret += rew; ep_len += 1; ret_out = ep_ret; len_out = ep_len; ep_ret *= 1-done; ep_len *= 1-done. */
+int ozl_episode_stats(int64_t n, const float* rew, const int64_t* done, float* ep_ret, int32_t* ep_len,
+                      float* ret_out, int32_t* len_out, void* stream);
+
 const char* ozl_last_error(void);
 int ozl_abi_version(void);
 

@@ -53,6 +53,18 @@ class OzlCfg(C.Structure):
         return self
 
 
+class OzlPvArgs(C.Structure):
+    """Mirror of `struct ozl_pv_args` (include/ouzelum_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64), ("x9xN", C.c_void_p), ("P81xN", C.c_void_p), ("accel3", C.c_void_p), ("quat4", C.c_void_p),
+        ("pos_meas3", C.c_void_p), ("vel_meas3", C.c_void_p), ("pos_mask", C.c_void_p), ("vel_mask", C.c_void_p),
+        ("dt", C.c_float), ("acc_var", C.c_float * 3), ("pos_var", C.c_float * 3), ("vel_var", C.c_float * 3),
+        ("pos_var_given", C.c_int32), ("vel_var_given", C.c_int32), ("flip_qw", C.c_int32), ("do_predict", C.c_int32),
+        ("pos_period", C.c_uint32), ("pos_phase", C.c_uint32), ("vel_period", C.c_uint32), ("vel_phase", C.c_uint32),
+        ("iter_base", C.c_uint64),
+    ]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ozl_abi_version": (C.c_int, []),
@@ -70,6 +82,16 @@ _SIGS = {
     "ozl_get_step_count": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "ozl_set_step_count": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_metrics_read": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "ozl_lee_control": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_float), _P, _P, _P]),
+    "ozl_pv_init": (C.c_int, [C.c_int64, _P, _P, _P]),
+    "ozl_pv_reset": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
+    "ozl_pv_step": (C.c_int, [C.POINTER(OzlPvArgs), _P]),
+    "ozl_ekf_init": (C.c_int, [C.c_int64, _P, _P, _P]),
+    "ozl_ekf_set_q": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
+    "ozl_ekf_update": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P]),
+    "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
+                                        C.c_int32, _P, _P, _P]),
+    "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

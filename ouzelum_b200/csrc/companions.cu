@@ -1,0 +1,292 @@
+// Companion kernels of the env step: Lee controllers (K4), PV Kalman filter (K3), attitude EKF (K2), sensor-fault
+// model on arbitrary vectors (K7), episode statistics (part of K6).  One env per thread; see the .cuh files for the math.
+#include "internal.h"
+#include "lee_control.cuh"
+#include "filters.cuh"
+
+namespace ozl {
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------ K4
+__global__ void __launch_bounds__(128)
+lee_control_kernel(int mode, int64_t n, const float* __restrict__ state13, const float* __restrict__ cmd4, const LeeGains g,
+                   float* __restrict__ thrust, float* __restrict__ torque3) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* s = state13 + i * 13;
+    const float p[3] = {s[0], s[1], s[2]}, q[4] = {s[3], s[4], s[5], s[6]}, v[3] = {s[7], s[8], s[9]}, w[3] = {s[10], s[11], s[12]};
+    const float4 c4 = reinterpret_cast<const float4*>(cmd4)[i];
+    const float cmd[4] = {c4.x * g.scale[0], c4.y * g.scale[1], c4.z * g.scale[2], c4.w * g.scale[3]};   // controller.py:47
+    float th, tq[3];
+    lee_control(mode, p, q, v, w, cmd, g, th, tq);
+    thrust[i] = th;
+    torque3[i * 3 + 0] = tq[0]; torque3[i * 3 + 1] = tq[1]; torque3[i * 3 + 2] = tq[2];
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+struct PVArgs {
+    int64_t n;
+    float* x;            // [9][n]
+    float* P;            // [81][n]
+    const float* accel;  // [n,3]
+    const float* quat;   // [n,4]
+    const float* pos_meas;   // [n,3] or null
+    const float* vel_meas;   // [n,3] or null
+    const uint8_t* pos_mask; // [n] or null
+    const uint8_t* vel_mask; // [n] or null
+    float dt, dt2;
+    float acc_var[3], pos_var[3], vel_var[3];
+    int flip_qw, do_predict;
+    uint32_t pos_period, pos_phase, vel_period, vel_phase;   // used when the mask pointer is null (0 = never)
+    uint64_t iter_base;                                        // global iteration index of env 0 (tasks/ekf_lee_landed.py:425-440)
+};
+
+__device__ __forceinline__ void pv_load(const PVArgs& a, int64_t i, PV& s) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s.x[k] = a.x[(int64_t)k * a.n + i];
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) s.P[r][c] = a.P[(int64_t)(r * 9 + c) * a.n + i];
+}
+__device__ __forceinline__ void pv_store(const PVArgs& a, int64_t i, const PV& s) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.x[(int64_t)k * a.n + i] = s.x[k];
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a.P[(int64_t)(r * 9 + c) * a.n + i] = s.P[r][c];
+}
+
+__global__ void __launch_bounds__(128)
+pv_step_kernel(const PVArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    PV s;
+    pv_load(a, i, s);
+    if (a.do_predict) {
+        const float acc[3] = {a.accel[i * 3], a.accel[i * 3 + 1], a.accel[i * 3 + 2]};
+        const float4 q4 = reinterpret_cast<const float4*>(a.quat)[i];
+        float q[4];
+        if (a.flip_qw) { q[0] = q4.w; q[1] = q4.x; q[2] = q4.y; q[3] = q4.z; }     // xyzw -> wxyz (PVFilter.py:32-33)
+        else { q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w; }
+        pv_predict(s, acc, q, a.dt, a.dt2, a.acc_var);
+    }
+    const uint64_t k = a.iter_base + (uint64_t)i;
+    bool pos_fix = false, vel_fix = false;
+    if (a.pos_meas) pos_fix = a.pos_mask ? (a.pos_mask[i] != 0) : (a.pos_period && (k % a.pos_period) == a.pos_phase);
+    if (a.vel_meas) vel_fix = a.vel_mask ? (a.vel_mask[i] != 0) : (a.vel_period && (k % a.vel_period) == a.vel_phase);
+    if (pos_fix) {                                                                  // ekf_lee_landed.py:428-433
+        const float z[3] = {a.pos_meas[i * 3], a.pos_meas[i * 3 + 1], a.pos_meas[i * 3 + 2]};
+        pv_correct<0>(s, z, a.pos_var);
+    }
+    if (vel_fix) {                                                                  // ekf_lee_landed.py:435-440
+        const float z[3] = {a.vel_meas[i * 3], a.vel_meas[i * 3 + 1], a.vel_meas[i * 3 + 2]};
+        pv_correct<3>(s, z, a.vel_var);
+    }
+    pv_store(a, i, s);
+}
+
+__global__ void pv_init_kernel(int64_t n, float* x, float* P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < 9; ++k) x[(int64_t)k * n + i] = 0.0f;                        // PVFilter.py:11
+    for (int k = 0; k < 81; ++k) P[(int64_t)k * n + i] = (k / 9 == k % 9) ? 1000.0f : 0.0f;   // PVFilter.py:12
+}
+
+// re-seed the state of reset envs with the true position / velocity (tasks/ekf_lee_landed.py:353-358)
+__global__ void pv_reset_kernel(int64_t n, float* x, const int64_t* flags, const float* root13) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (flags && flags[i] == 0)) return;
+    const float* r = root13 + i * 13;
+    for (int k = 0; k < 3; ++k) {
+        x[(int64_t)k * n + i] = r[k];
+        x[(int64_t)(3 + k) * n + i] = r[7 + k];
+        x[(int64_t)(6 + k) * n + i] = 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(128)
+ekf_update_kernel(int64_t n, double* __restrict__ q, double* __restrict__ P, const float* __restrict__ gyr,
+                  const float* __restrict__ ang, int ang_xyzw, double Dt, double g_noise, double s_eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EKF4 s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.q[k] = q[(int64_t)k * n + i];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = P[(int64_t)k * n + i];
+    const double g[3] = {(double)gyr[i * 3], (double)gyr[i * 3 + 1], (double)gyr[i * 3 + 2]};
+    const float4 a4 = reinterpret_cast<const float4*>(ang)[i];
+    double a[4];
+    if (ang_xyzw) { a[0] = a4.w; a[1] = a4.x; a[2] = a4.y; a[3] = a4.z; }        // root_quats[idx,[3,0,1,2]]
+    else { a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w; }
+    ekf_update(s, g, a, Dt, g_noise, s_eps);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[(int64_t)k * n + i] = s.q[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) P[(int64_t)k * n + i] = s.P[k / 4][k % 4];
+}
+
+__global__ void ekf_init_kernel(int64_t n, double* q, double* P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < 4; ++k) q[(int64_t)k * n + i] = (k == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < 16; ++k) P[(int64_t)k * n + i] = (k / 4 == k % 4) ? 1.0 : 0.0;      // ahrs_ekf.py:995
+}
+
+// Q_state[ids] = root_quats[ids][:, [3,0,1,2]]  (tasks/ekf_lee_landed.py:349-352)
+__global__ void ekf_set_q_kernel(int64_t n, double* q, const float* quat_xyzw, const int64_t* flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (flags && flags[i] == 0)) return;
+    const float4 v = reinterpret_cast<const float4*>(quat_xyzw)[i];
+    q[i] = v.w; q[n + i] = v.x; q[2 * n + i] = v.y; q[3 * n + i] = v.z;
+}
+
+// ------------------------------------------------------------------------------------------------ K7 (stand-alone)
+// POMDPWrapper.observation on an [n, d] float32 array (utils/POMDP.py:23-42): flicker = one draw per call blacks out
+// EVERY env; noise = element-wise U(1-s, 1+s).  Draws: philox(seed, env, step, P_OBSNOISE + j/4)[j%4]; the flicker draw
+// uses env word GLOBAL_ENV.  `stream_id` separates several uses within one step (gyro / accel / pos / vel ...).
+__global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float noise_lo, float noise_range, uint64_t seed,
+                             uint64_t step, uint32_t env_id_base, uint32_t stream_id, const float* __restrict__ in,
+                             float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool blackout = false;
+    if (mode == 1 || mode == 3) {
+        const uint4 r = draw(seed, GLOBAL_ENV, step, P_FLICKER + (stream_id << 8));
+        blackout = u01(r.x) <= flicker_p;
+    }
+    const uint32_t genv = env_id_base + (uint32_t)i;
+    for (int j0 = 0; j0 < d; j0 += 4) {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (mode >= 2) r = draw(seed, genv, step, (P_OBSNOISE + (uint32_t)(j0 >> 2)) + (stream_id << 8));
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < 4 && j0 + j < d; ++j) {
+            float v = blackout ? 0.0f : in[i * d + j0 + j];
+            if (mode >= 2) v = v * (u01(rr[j]) * noise_range + noise_lo);
+            out[i * d + j0 + j] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ episode statistics
+// RecordEpisodeStatisticsTorch.step (RPO-LSTM/utils.py:20-35): 6 element-wise launches -> 1
+__global__ void episode_stats_kernel(int64_t n, const float* __restrict__ rew, const int64_t* __restrict__ done,
+                                     float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, float* __restrict__ ret_out,
+                                     int32_t* __restrict__ len_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float r = ep_ret[i] + rew[i];
+    const int32_t l = ep_len[i] + 1;
+    ret_out[i] = r;
+    len_out[i] = l;
+    const int64_t dn = done[i];
+    ep_ret[i] = r * (float)(1 - dn);          // episode_returns *= 1 - dones
+    ep_len[i] = l * (int32_t)(1 - dn);
+}
+
+}  // namespace ozl
+
+using namespace ozl;
+
+#define OZL_N_CHECK(name)                                        \
+    if (n <= 0) return set_error(name ": n must be > 0");        \
+    cudaStream_t st = (cudaStream_t)stream;
+
+extern "C" int ozl_lee_control(int32_t mode, int64_t n, const float* state13, const float* cmd4, const float* gains16,
+                               float* thrust, float* torque3, void* stream) {
+    OZL_N_CHECK("ozl_lee_control");
+    if (mode < 0 || mode > 2) return set_error("Invalid controller name: mode %d (0 position, 1 velocity, 2 attitude)", mode);
+    if (!state13 || !cmd4 || !gains16 || !thrust || !torque3) return set_error("ozl_lee_control: NULL buffer");
+    if ((uintptr_t)cmd4 & 15) return set_error("ozl_lee_control: cmd4 must be 16-byte aligned");
+    LeeGains g;
+    for (int k = 0; k < 3; ++k) { g.kP[k] = gains16[k]; g.kV[k] = gains16[3 + k]; g.kR[k] = gains16[6 + k]; g.kO[k] = gains16[9 + k]; }
+    for (int k = 0; k < 4; ++k) g.scale[k] = gains16[12 + k];
+    lee_control_kernel<<<nblk(n, 128), 128, 0, st>>>(mode, n, state13, cmd4, g, thrust, torque3);
+    return check_cuda(cudaGetLastError(), "lee_control_kernel");
+}
+
+extern "C" int ozl_pv_init(int64_t n, float* x9xN, float* P81xN, void* stream) {
+    OZL_N_CHECK("ozl_pv_init");
+    if (!x9xN || !P81xN) return set_error("ozl_pv_init: NULL buffer");
+    pv_init_kernel<<<nblk(n, 256), 256, 0, st>>>(n, x9xN, P81xN);
+    return check_cuda(cudaGetLastError(), "pv_init_kernel");
+}
+
+extern "C" int ozl_pv_reset(int64_t n, float* x9xN, const int64_t* flags, const float* root13, void* stream) {
+    OZL_N_CHECK("ozl_pv_reset");
+    if (!x9xN || !root13) return set_error("ozl_pv_reset: NULL buffer");
+    pv_reset_kernel<<<nblk(n, 256), 256, 0, st>>>(n, x9xN, flags, root13);
+    return check_cuda(cudaGetLastError(), "pv_reset_kernel");
+}
+
+extern "C" int ozl_pv_step(const ozl_pv_args* a, void* stream) {
+    if (!a) return set_error("ozl_pv_step: args is NULL");
+    const int64_t n = a->n;
+    OZL_N_CHECK("ozl_pv_step");
+    if (!a->x9xN || !a->P81xN) return set_error("ozl_pv_step: NULL state buffer");
+    if (a->do_predict && (!a->accel3 || !a->quat4)) return set_error("ozl_pv_step: predict needs accel3 and quat4");
+    if (a->quat4 && ((uintptr_t)a->quat4 & 15)) return set_error("ozl_pv_step: quat4 must be 16-byte aligned");
+    PVArgs k;
+    k.n = n; k.x = a->x9xN; k.P = a->P81xN; k.accel = a->accel3; k.quat = a->quat4;
+    k.pos_meas = a->pos_meas3; k.vel_meas = a->vel_meas3; k.pos_mask = a->pos_mask; k.vel_mask = a->vel_mask;
+    k.dt = a->dt;
+    k.dt2 = (float)((double)a->dt * (double)a->dt);       // python `dt**2` (double), then float32 against the tensor
+    for (int j = 0; j < 3; ++j) {
+        k.acc_var[j] = a->acc_var[j];
+        k.pos_var[j] = a->pos_var_given ? a->pos_var[j] : 0.0f;       // PVFilter.py:96-99
+        k.vel_var[j] = a->vel_var_given ? a->vel_var[j] : 0.0f;       // PVFilter.py:76-79 (the reference passes gps_var=None => 0)
+    }
+    k.flip_qw = a->flip_qw; k.do_predict = a->do_predict;
+    k.pos_period = a->pos_period; k.pos_phase = a->pos_phase; k.vel_period = a->vel_period; k.vel_phase = a->vel_phase;
+    k.iter_base = a->iter_base;
+    pv_step_kernel<<<nblk(n, 128), 128, 0, st>>>(k);
+    return check_cuda(cudaGetLastError(), "pv_step_kernel");
+}
+
+extern "C" int ozl_ekf_init(int64_t n, double* q4xN, double* P16xN, void* stream) {
+    OZL_N_CHECK("ozl_ekf_init");
+    if (!q4xN || !P16xN) return set_error("ozl_ekf_init: NULL buffer");
+    ekf_init_kernel<<<nblk(n, 256), 256, 0, st>>>(n, q4xN, P16xN);
+    return check_cuda(cudaGetLastError(), "ekf_init_kernel");
+}
+
+extern "C" int ozl_ekf_set_q(int64_t n, double* q4xN, const float* quat_xyzw, const int64_t* flags, void* stream) {
+    OZL_N_CHECK("ozl_ekf_set_q");
+    if (!q4xN || !quat_xyzw) return set_error("ozl_ekf_set_q: NULL buffer");
+    ekf_set_q_kernel<<<nblk(n, 256), 256, 0, st>>>(n, q4xN, quat_xyzw, flags);
+    return check_cuda(cudaGetLastError(), "ekf_set_q_kernel");
+}
+
+extern "C" int ozl_ekf_update(int64_t n, double* q4xN, double* P16xN, const float* gyr3, const float* ang4, int32_t ang_xyzw,
+                              double Dt, double g_noise, void* stream) {
+    OZL_N_CHECK("ozl_ekf_update");
+    if (!q4xN || !P16xN || !gyr3 || !ang4) return set_error("ozl_ekf_update: NULL buffer");
+    if ((uintptr_t)ang4 & 15) return set_error("ozl_ekf_update: ang4 must be 16-byte aligned");
+    ekf_update_kernel<<<nblk(n, 128), 128, 0, st>>>(n, q4xN, P16xN, gyr3, ang4, ang_xyzw, Dt, g_noise, 0.0000001);
+    return check_cuda(cudaGetLastError(), "ekf_update_kernel");
+}
+
+extern "C" int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step,
+                                     int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream) {
+    OZL_N_CHECK("ozl_pomdp_observation");
+    if (mode < 1 || mode > 3)
+        return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");   // POMDP.py:19-20
+    if (d <= 0 || d > 64 || !in || !out) return set_error("ozl_pomdp_observation: bad arguments");
+    const float flick = (mode == 3) ? 0.1f : pomdp_prob;                                   // POMDP.py:16-18
+    const float lo = (float)(1.0 - (double)pomdp_prob), hi = (float)(1.0 + (double)pomdp_prob);
+    pomdp_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d, mode, flick, lo, hi - lo, seed, step, (uint32_t)env_id_base,
+                                               (uint32_t)stream_id, in, out);
+    return check_cuda(cudaGetLastError(), "pomdp_kernel");
+}
+
+extern "C" int ozl_episode_stats(int64_t n, const float* rew, const int64_t* done, float* ep_ret, int32_t* ep_len,
+                                 float* ret_out, int32_t* len_out, void* stream) {
+    OZL_N_CHECK("ozl_episode_stats");
+    if (!rew || !done || !ep_ret || !ep_len || !ret_out || !len_out) return set_error("ozl_episode_stats: NULL buffer");
+    episode_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, rew, done, ep_ret, ep_len, ret_out, len_out);
+    return check_cuda(cudaGetLastError(), "episode_stats_kernel");
+}

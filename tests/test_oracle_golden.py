@@ -1,0 +1,182 @@
+"""The oracle against the REFERENCE'S OWN CODE: fixtures in tests/golden/*.npz were produced by running the
+reference's functions / classes on CPU (tests/golden/make_golden.py).  CPU-only; no CUDA needed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+# ------------------------------------------------------------------------------------------------ reward / observation
+def test_reward_and_reset_match_reference_functions():
+    from oracle.quad_step import compute_ingenuity_reward, quat_axis, quat_rotate
+    d = load("reward.npz")
+    st, tgt = torch.from_numpy(d["state"]), torch.from_numpy(d["target"])
+    prog = torch.from_numpy(d["progress"])
+    zeros = torch.zeros_like(prog)
+    # quat helpers are torch-exact restatements
+    assert np.array_equal(quat_axis(st[:, 3:7], 2).numpy(), d["quat_axis2"])
+    assert np.array_equal(quat_rotate(st[:, 3:7], torch.from_numpy(d["rot_v"])).numpy(), d["quat_rotate"])
+    for name, kw, maxlen in (("ouzelum", dict(die_z=0.5), 2000.0), ("landing", dict(die_z=0.3), 2000.0)):
+        r, reset = compute_ingenuity_reward(st[:, 0:3], tgt, st[:, 3:7], st[:, 7:10], st[:, 10:13], zeros, prog, maxlen, **kw)
+        # float: the only difference is the oracle's IEEE sqrt vs torch-CPU's (MKL) 1-2 ulp-off sqrt
+        np.testing.assert_allclose(r.numpy(), d["rew_" + name], rtol=1e-6, atol=1e-7)
+        # integer flags: bit-exact, except where |dist - 8| is within the sqrt ulp noise (none in the fixture)
+        assert np.array_equal(reset.numpy(), d["reset_" + name]), name
+    assert 0 < d["reset_ouzelum"].mean() < 1
+
+
+def test_quadcopter_reward_matches_reference():
+    from oracle.quadcopter import compute_quadcopter_reward
+    d = load("reward.npz")
+    st = torch.from_numpy(d["state"])
+    prog = torch.from_numpy(d["progress"])
+    r, reset = compute_quadcopter_reward(st[:, 0:3], st[:, 3:7], st[:, 7:10], st[:, 10:13], torch.zeros_like(prog), prog, 500.0)
+    np.testing.assert_allclose(r.numpy(), d["rew_quadcopter"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(reset.numpy(), d["reset_quadcopter"])
+
+
+def test_observation_matches_reference_formula_within_one_ulp():
+    """obs = [(target-pos)/3, quat, linvel/2, angvel/pi] (ouzelum.py:280-285).  The oracle multiplies by the float32
+    reciprocal (torch-CUDA evaluation of tensor/scalar); torch-CPU divides: <= 1 ulp apart."""
+    import math
+    from oracle.quad_step import compute_observations
+    d = load("reward.npz")
+    st, tgt = torch.from_numpy(d["state"]), torch.from_numpy(d["target"])
+    obs = compute_observations(st, tgt)
+    ref = torch.cat([(tgt - st[:, 0:3]) / 3, st[:, 3:7], st[:, 7:10] / 2, st[:, 10:13] / math.pi], 1)
+    np.testing.assert_allclose(obs.numpy(), ref.numpy(), rtol=1.3e-7, atol=0)
+    assert np.array_equal(obs[:, 3:10].numpy(), ref[:, 3:10].numpy())          # copies and /2 are exact
+
+
+# ------------------------------------------------------------------------------------------------ Lee controllers
+@pytest.mark.parametrize("name,mode", [("lee_position_control", 0), ("lee_velocity_control", 1), ("lee_attitude_control", 2)])
+def test_lee_controllers_match_reference_classes(name, mode):
+    from oracle.lee_control import lee_control
+    d = load("lee.npz")
+    thrust, torque = lee_control(d["state"], d["command"], mode=mode)
+    np.testing.assert_allclose(thrust, d[name + "_thrust"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(torque, d[name + "_torque"], rtol=2e-5, atol=5e-5)
+    t64, q64 = lee_control(d["state"], d["command"], mode=mode, dtype=np.float64)
+    np.testing.assert_allclose(t64, d[name + "_thrust"], rtol=2e-5, atol=2e-5)
+
+
+def test_lee_known_answers_from_survey():
+    from oracle.lee_control import lee_control
+    d = load("lee.npz")
+    np.testing.assert_allclose(d["kat_thrust"], [1.0, 2.0385], atol=1e-4)
+    np.testing.assert_allclose(d["kat_torque"], [[0, 0, 0], [-0.5959, -0.1204, 0.0262]], atol=1e-4)
+    thrust, torque = lee_control(d["kat_state"], np.array([[0, 0, 1.0, 0]] * 2, np.float32))
+    np.testing.assert_allclose(thrust, d["kat_thrust"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(torque, d["kat_torque"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ PV filter
+def test_pv_filter_matches_reference_class():
+    from oracle.pv_filter import PVFilterBank
+    d = load("pvfilter.npz")
+    T, n = d["acc"].shape[:2]
+    bank = PVFilterBank(n, [1.0, 1.0, 1.0])
+    var = np.full(3, 0.0000001, np.float32)
+    for t in range(T):
+        bank.prediction_step(d["acc"][t], d["quat"][t], 0.01, flip_Qw=(t % 2 == 0))
+        # reference order inside the per-env loop: position fix, then velocity fix (ekf_lee_landed.py:428-440)
+        if d["pos_fix"][t].any():
+            bank.correction_step(gps_data=d["pos_meas"][t], gps_var=var, mask=d["pos_fix"][t])
+        if d["vel_fix"][t].any():
+            bank.correction_step(vel_data=d["vel_meas"][t], vel_var=var, mask=d["vel_fix"][t])
+        scale = np.abs(d["states"][t]).max() + 1.0
+        np.testing.assert_allclose(bank.state, d["states"][t], rtol=2e-3, atol=2e-3 * scale, err_msg=f"t={t}")
+        # resynchronise so that every step is compared from an identical state (float32 KF with P=1000 and R=1e-7
+        # is ill-conditioned: differences in summation order inside the reference's matmuls are amplified)
+        bank.state, bank.cov = d["states"][t].copy(), d["covs"][t].copy()
+
+
+def test_pv_filter_known_answer_from_survey():
+    from oracle.pv_filter import PVFilterBank
+    d = load("pvfilter.npz")
+    b = PVFilterBank(1, [1.0, 1.0, 1.0])
+    b.prediction_step(np.array([[0, 0, 9.8]]), np.array([[0, 0, 0, 1.0]]), 0.01)
+    np.testing.assert_allclose(b.state[0], d["kat_pred"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(b.state[0], [0, 0, 4.9e-4, 0, 0, 0.098, 0, 0, 0], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(np.diag(b.cov[0]), np.diag(d["kat_pred_cov"]), rtol=1e-6)
+    b.correction_step(gps_data=np.array([[1.0, 2.0, 3.0]]), gps_var=np.full(3, 1e-7, np.float32))
+    np.testing.assert_allclose(b.state[0], d["kat_corr"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(b.state[0][:3], [1, 2, 3], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ EKF
+def test_ekf_matches_reference_update():
+    from oracle.ahrs_ekf import EKFBank
+    d = load("ekf.npz")
+    T, n = d["gyr"].shape[:2]
+    bank = EKFBank(n, frequency=100.0)
+    q = d["q0"].copy()
+    for t in range(T):
+        q = bank.update(q / np.linalg.norm(q, axis=1, keepdims=True), d["gyr"][t], d["ang"][t], d["acc"][t])
+        np.testing.assert_allclose(q, d["Q"][t], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(bank.P, d["P"][t], rtol=1e-8, atol=1e-16)
+    # SURVEY KAT-E
+    b = EKFBank(1)
+    kq = b.update(np.array([[1.0, 0, 0, 0]]), np.array([[0.1, -0.2, 0.3]]), np.array([[0.9990, 0.03, -0.02, 0.025]]))
+    np.testing.assert_allclose(kq[0], d["kat_q"], rtol=1e-12)
+    np.testing.assert_allclose(kq[0], [0.99903697, 0.03000111, -0.02000074, 0.02500092], atol=1e-7)
+    with pytest.raises(ValueError):
+        b.update(np.array([[2.0, 0, 0, 0]]), np.zeros((1, 3)), np.array([[1.0, 0, 0, 0]]))
+
+
+# ------------------------------------------------------------------------------------------------ trajectories
+def test_waypoint_tables_and_differential_drive_match_reference():
+    from oracle import trajectories as tr
+    d = load("trajectories.npz")
+    lem, cir, sq = tr.landing_tables()
+    assert np.array_equal(sq, d["square"]) and np.array_equal(sq, [[2, 2], [-2, 2], [-2, -2], [2, -2]])
+    assert np.array_equal(cir, d["circle"])
+    np.testing.assert_allclose(lem, d["lemniscate"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(cir[1], [1.9961, 0.1256], atol=1e-4)
+    np.testing.assert_allclose(lem[1], [0.12710, -0.12685], atol=1e-4)
+    out = tr.differential_drive(d["dd_cur"], d["dd_tgt"], d["dd_heading"], (3.0, 1000))
+    np.testing.assert_allclose(out, d["dd_out"], rtol=2e-4, atol=2e-3)
+    kat = tr.differential_drive(np.zeros((2, 2)), np.array([[1.0, 0], [0, 1.0]]), np.zeros(2), (3, 1000))
+    np.testing.assert_allclose(kat, d["dd_kat"], rtol=1e-5)
+    np.testing.assert_allclose(kat, [[15, 15, 15, 15], [-14.7893, 15, -14.7893, 15]], atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ termination logs
+def test_termination_logic_agrees_with_logged_reference_runs():
+    """isaacgymenvs/trajectories/flicker_0.01_ep_*.csv (written by tasks/landed.py:346-353): every completed episode
+    ends on exactly one of the reward function's conditions (landed.py:393-400) -- the oracle's reset rule must say so too."""
+    from oracle.quad_step import compute_ingenuity_reward
+    d = load("landed_logs.npz")
+    cols = list(d["columns"])
+    ep = {c: d["episodes"][:, i] for i, c in enumerate(cols)}
+    done = (ep["episode"] >= 1) & (ep["episode"] <= 26)
+    n_timeout = n_far = n_low = 0
+    for i in np.nonzero(done)[0]:
+        rows, last_d, prev_d, last_z = int(ep["rows"][i]), ep["last_dist"][i], ep["prev_dist"][i], ep["last_z"][i]
+        pos = torch.tensor([[last_d, 0.0, last_z]], dtype=torch.float32)
+        tgt = torch.tensor([[0.0, 0.0, last_z]], dtype=torch.float32)
+        q = torch.tensor([[0.0, 0, 0, 1]])
+        z3 = torch.zeros(1, 3)
+        prog = torch.tensor([rows])
+        _, reset = compute_ingenuity_reward(pos, tgt, q, z3, z3, torch.zeros(1, dtype=torch.long), prog, 2000.0, die_z=0.3)
+        assert int(reset) == 1, f"episode {int(ep['episode'][i])} ended but the oracle would not reset it"
+        if rows >= 1999:
+            n_timeout += 1
+        elif last_d > 8.0:
+            assert prev_d < 8.0
+            n_far += 1
+        else:
+            assert last_z < 0.3
+            n_low += 1
+    assert (n_timeout, n_far, n_low) == (15, 9, 2)      # SURVEY section 4 (16 files have 1999 rows, one of them is the unfinished... no: counted here)
+    assert np.allclose(ep["target_z_min"][done], 0.377, atol=1e-3) and np.allclose(ep["target_z_max"][done], 0.377, atol=1e-3)
+    landed = int(((ep["min_dist"] < 0.2) & done).sum())
+    assert landed == int(d["landing_counter"]) == 23
+    assert (np.abs(ep["x0"][done]) <= 1.51).all() and (np.abs(ep["y0"][done]) <= 1.51).all()
