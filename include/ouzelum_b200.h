@@ -72,7 +72,11 @@ typedef struct ozl_cfg {
     float pomdp_prob;             /* flicker probability                                          POMDP.py:8      */
     float noise_sigma;            /* multiplicative noise U(1-s, 1+s)                             POMDP.py:9-10   */
     int32_t collect_metrics;      /* 1: accumulate the episode/reward metrics vector (ozl_metrics_read)           */
-    int32_t reserved1;
+    int32_t plate_enable;         /* 1: inelastic landing plate under the target (landing family; new, see DESIGN) */
+    float plate_z;                /* plate height (0.377 = Husky top plate, landing.py:76)                        */
+    float plate_radius;           /* horizontal reach of the plate around the target                              */
+    float land_cutoff;            /* >0: zero the wrench within this distance of the target and flag a landing
+                                     (tasks/landed.py:288-295 0.2, lee_landed.py:318-322 0.2, ekf_lee_landed.py:508-515 0.25) */
 } ozl_cfg;
 
 typedef struct ozl_env ozl_env;   /* opaque */
@@ -103,6 +107,17 @@ int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream);
 int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
              uint8_t* timeout, float* ep_ret, void* stream);
 
+/* Same step with the target supplied by the caller every step instead of being re-sampled in-kernel: the landing
+ * family, whose target rides on a ground vehicle (tasks/landing.py:373-374, lando.py, landed.py).  target3 [N,3] f32. */
+int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,
+                      int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
+
+/* Same step actuated by a body wrench instead of rotor thrust-rate commands: wrench4 [N,4] f32 = (fz, tx, ty, tz) on
+ * the base link in LOCAL_SPACE, as the classical-control tasks apply it (tasks/lee_landed.py:316-330,
+ * tasks/ekf_lee_landed.py:504-530).  No action clamp; target3 may be NULL (use the stored target). */
+int ozl_step_wrench(ozl_env* env, const float* wrench4, const float* target3, float* obs, float* rew,
+                    int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
+
 /* Mode-B throughput entry: K steps in ONE launch, state held in registers, actions a = 2u-1 drawn
  * in-kernel from the counter RNG; obs/rew are written for the LAST step only, reset/progress are
  * carried.  No reference counterpart (SURVEY 8d "mode B"). */
@@ -114,7 +129,7 @@ int ozl_get_state(ozl_env* env, float* root13, float* thrust4, float* target3, f
 int ozl_set_state(ozl_env* env, const float* root13, const float* thrust4, const float* target3,
                   const float* ep_ret, void* stream);
 /* per-env parameters: params7 [N,7] = mass, ixx, iyy, izz, arm, thrust_scale, fault_effectiveness;
- * fault2 [N,2] i32 = fault rotor id, fault onset step (>= 2^29: never). */
+ * fault2 [N,2] i32 = fault rotor id, fault onset step (0x1FFFFFFF: never). */
 int ozl_get_params(ozl_env* env, float* params7, int32_t* fault2, void* stream);
 int ozl_set_params(ozl_env* env, const float* params7, const int32_t* fault2, void* stream);
 
@@ -123,7 +138,7 @@ int ozl_get_step_count(ozl_env* env, uint64_t* out, void* stream);
 int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream);
 
 /* Metrics vector accumulated since the last clearing read (16 doubles, device pointer `out16`):
- *  [0] sum reward  [1] sum episode return of finished episodes  [2..7] reserved
+ *  [0] sum reward  [1] sum episode return of finished episodes  [2] episodes that ended after a landing  [3..7] reserved
  *  [8] env-steps  [9] finished episodes  [10] sum of finished episode lengths  [11] time-outs
  *  [12] dist>die_dist  [13] z<die_z  [14] env-steps with an active rotor fault  [15] resets applied
  * Replaces RecordEpisodeStatisticsTorch + the trainer's Python scan (RPO-LSTM/utils.py:20-35, main.py:105-113). */
@@ -142,6 +157,10 @@ int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream);
  *   thrust [n] f32, torque3 [n,3] f32 ("m*g normalised thrust and inertia normalised torques") */
 int ozl_lee_control(int32_t mode, int64_t n, const float* state13, const float* cmd4, const float* gains16,
                     float* thrust, float* torque3, void* stream);
+/* Same controller, output packed as the body wrench the classical tasks apply: wrench4 [n,4] f32 =
+ * (thrust_scale * thrust, tx, ty, tz) with thrust_scale = m g = 2 * 9.81 (tasks/lee_landed.py:296,313-314). */
+int ozl_lee_wrench(int32_t mode, int64_t n, const float* state13, const float* cmd4, const float* gains16,
+                   float thrust_scale, float* wrench4, void* stream);
 
 /* Position/velocity/accel-bias Kalman filter bank.  State planes are SoA: x9xN = [9][n] f32, P81xN = [81][n] f32
  * (row-major 9x9 per env, full matrix -- the reference's (I-KH)P update is not symmetric in float32).
@@ -193,8 +212,37 @@ int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, 
 int ozl_episode_stats(int64_t n, const float* rew, const int64_t* done, float* ep_ret, int32_t* ep_len,
                       float* ret_out, int32_t* len_out, void* stream);
 
+/* Waypoint-following ground vehicle that carries the landing target (kinematic differential drive).
+ * Replaces Landing.set_husky_actions / reset_completed_trajectories (isaacgymenvs/tasks/landing.py:208-244,319-364),
+ * differential_drive (utils/controllers.py:15-43) and the target-on-vehicle rule (landing.py:373-374).
+ *   pose4 [n,4] f32 = x, y, heading, scale*direction      idx2 [n,2] i32 = trajectory id, waypoint index
+ *   tables204x2 [204,2] f32 = lemniscate(4,100) | circle(2,100) | square(4,8)   (utils/trajectories.py, landing.py:108-112)
+ *   reset [n] i64 or NULL: drone reset flags (a vehicle beyond respawn_limit is re-spawned, landing.py:263-270)
+ *   wheels4 [n,4] f32 out or NULL (right,left,right,left), target3 [n,3] f32 out */
+typedef struct ozl_husky_args {
+    int64_t n;
+    float* pose4;
+    int32_t* idx2;
+    const float* tables204x2;
+    const int64_t* reset;
+    float* wheels4;
+    float* target3;
+    uint64_t seed, step;
+    int64_t env_id_base;
+    float dt;             /* 0.01                                      */
+    float dist_thresh;    /* 0.2        landing.py:319                 */
+    float kp_lin, kp_ang; /* 3.0, 1000  landing.py:362                 */
+    float ang_thresh;     /* 0.005      utils/controllers.py:16        */
+    float x_offset;       /* +0.08 (landing.py:374) / -0.08 (ekf_lee_landed.py:629) */
+    float target_z;       /* 0.377      landing.py:76                  */
+    float respawn_limit;  /* 2 * envSpacing  landing.py:266-267        */
+} ozl_husky_args;
+int ozl_husky_init(const ozl_husky_args* args, void* stream);
+int ozl_husky_step(const ozl_husky_args* args, void* stream);
+
 const char* ozl_last_error(void);
 int ozl_abi_version(void);
+int ozl_cfg_size(void);            /* sizeof(ozl_cfg): lets a binding verify its struct mirror */
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ def default_cfg(num_envs, **over):
         fault_mode=0, fault_eff_lo=0.0, fault_eff_range=0.5,
         dr_enable=0, dr_lo=0.8, dr_range=1.2 - 0.8,
         pomdp_mode=POMDP_NONE, pomdp_prob=0.0, noise_sigma=0.0,
+        plate_enable=0, plate_z=0.377, plate_radius=0.35, land_cutoff=0.0,
     )
     cfg.update(over)
     return cfg
@@ -180,8 +181,9 @@ class QuadStepOracle:
             self.params[:, j] = float(np.float32(cfg[k])) if dtype == torch.float32 else cfg[k]
         self.params[:, 5] = 1.0
         self.fault_rotor = torch.zeros(n, dtype=torch.int64)
-        self.fault_onset = torch.full((n,), 0x3FFFFFFF, dtype=torch.int64)   # never, until a reset draws one
+        self.fault_onset = torch.full((n,), 0x1FFFFFFF, dtype=torch.int64)   # never, until a reset draws one
         self.fault_eff = torch.ones(n, dtype=dtype)
+        self.landed = torch.zeros(n, dtype=torch.bool)        # came within land_cutoff of the target this episode
         # VecTask.allocate_buffers (vec_task.py:254-277)
         self.obs_buf = z(n, 13)
         self.rew_buf = z(n)
@@ -192,6 +194,7 @@ class QuadStepOracle:
         # metrics (kernel K6): sums in float64, counts in int64
         self.msum = np.zeros(8, dtype=np.float64)
         self.mcnt = np.zeros(8, dtype=np.int64)
+        self.mlanded = 0
         self.env_ids = np.arange(n, dtype=np.uint64) + np.uint64(cfg.get("env_id_base", 0))
 
     # ------------------------------------------------------------------ helpers
@@ -203,10 +206,14 @@ class QuadStepOracle:
         return torch.from_numpy(px.u01(r)).to(self.dtype)
 
     # ------------------------------------------------------------------ step
-    def step(self, actions):
+    def step(self, actions, target_in=None, act_mode=0):
+        """act_mode 0: rotor thrust-rate actions (ouzelum.py:237-244); 1: body wrench (fz,tx,ty,tz) on the base link
+        (lee_landed.py:316-330).  target_in [N,3]: externally driven target (landing.py:373-374)."""
         cfg, c, dt_ = self.cfg, self._c, self.dtype
         seed, t = cfg.get("seed", 0), self.step_count
-        a = torch.clamp(actions.to(dt_), -cfg["clip_actions"], cfg["clip_actions"])     # vec_task.py:327
+        a = actions.to(dt_)
+        if act_mode == 0:
+            a = torch.clamp(a, -cfg["clip_actions"], cfg["clip_actions"])                 # vec_task.py:327
         prog, rst = self.progress_buf, self.reset_buf != 0
 
         # ---- pre_physics_step: target resample (ouzelum.py:221-224) and reset (ouzelum.py:226-229)
@@ -217,6 +224,9 @@ class QuadStepOracle:
         u = [self._u(r) for r in (r0, r1, r2)]
         new_t = torch.stack([u[j] * c(cfg["target_scale"][j]) + c(cfg["target_off"][j]) for j in range(3)], -1)
         self.target = torch.where(resample[:, None], new_t, self.target)
+        landed_episode = rst & self.landed                                            # landed.py:265-271
+        self.landed = self.landed & ~rst
+        self._landed_episode = landed_episode
 
         r0, r1, r2, _ = px.draw(seed, self.env_ids, t, px.P_SPAWN)
         u = [self._u(r) for r in (r0, r1, r2)]
@@ -243,6 +253,23 @@ class QuadStepOracle:
                                 for j in range(6)], -1)
             self.params = torch.where(rst[:, None], newp, self.params)
 
+        # landing detector (landed.py:288-295): pre-step position, target as left by the previous step
+        cut = torch.zeros_like(rst)
+        if cfg.get("land_cutoff", 0.0) > 0:
+            d0 = self.target - self.root[:, 0:3]
+            cut = ieee_sqrt((d0[:, 0] * d0[:, 0] + d0[:, 1] * d0[:, 1]) + d0[:, 2] * d0[:, 2]) < c(cfg["land_cutoff"])
+            self.landed = self.landed | cut
+        if target_in is not None:
+            self.target = target_in.to(dt_).clone()
+        if act_mode == 1:
+            zero = torch.zeros_like(a[:, 0])
+            off = rst | cut
+            fz = torch.where(off, zero, a[:, 0])
+            tau_b = [torch.where(off, zero, a[:, 1 + j]) for j in range(3)]
+            self.thrust = torch.where(rst[:, None], torch.zeros_like(self.thrust), self.thrust)
+            fault_active = torch.zeros_like(rst)
+            self._simulate(None, wrench=(fz, tau_b))
+            return self._post(prog, rst, fault_active)
         # ---- thrust command (ouzelum.py:237-248)
         thr = self.thrust + c(cfg["thrust_rate"]) * a
         thr = torch.max(torch.min(thr, c(cfg["thrust_max"])), c(0.0))
@@ -252,6 +279,7 @@ class QuadStepOracle:
         self.thrust = thr
         # rotor effectiveness (thrust scale from DR; single-rotor loss of effectiveness once progress >= onset)
         force = force * self.params[:, 5:6]
+        force = torch.where(cut[:, None], torch.zeros_like(force), force)
         fault_active = (prog >= self.fault_onset) if cfg["fault_mode"] else torch.zeros_like(rst)
         for i in range(4):
             hit = fault_active & (self.fault_rotor == i)
@@ -259,7 +287,19 @@ class QuadStepOracle:
 
         # ---- gym.simulate replacement
         self._simulate(force)
+        return self._post(prog, rst, fault_active)
 
+    def _post(self, prog, rst, fault_active):
+        cfg, c, dt_ = self.cfg, self._c, self.dtype
+        seed, t = cfg.get("seed", 0), self.step_count
+        if cfg.get("plate_enable", 0):
+            # landing plate (new; the reference relies on PhysX contact with the Husky's top plate)
+            ddx, ddy = self.target[:, 0] - self.root[:, 0], self.target[:, 1] - self.root[:, 1]
+            hit = (self.root[:, 2] < c(cfg["plate_z"])) & ((ddx * ddx + ddy * ddy) <= c(cfg["plate_radius"] ** 2))
+            stopped = self.root.clone()
+            stopped[:, 2] = c(cfg["plate_z"])
+            stopped[:, 7:13] = 0
+            self.root = torch.where(hit[:, None], stopped, self.root)
         # ---- post_physics_step (ouzelum.py:253-261)
         prog = prog + 1
         root = self.root
@@ -307,6 +347,7 @@ class QuadStepOracle:
         self.mcnt[5] += int((root[:, 2] < cfg["die_z"]).sum())
         self.mcnt[6] += int(fault_active.sum())
         self.mcnt[7] += int(rst.sum())
+        self.mlanded += int(self._landed_episode.sum())
         self.returned_ep_ret = ep_ret.clone()
         self.ep_ret = torch.where(done, torch.zeros_like(ep_ret), ep_ret)
 
@@ -315,7 +356,7 @@ class QuadStepOracle:
         return self.obs_buf, self.rew_buf, self.reset_buf, self.timeout_buf
 
     # ------------------------------------------------------------------ rigid body
-    def _simulate(self, force):
+    def _simulate(self, force, wrench=None):
         cfg, c = self.cfg, self._c
         root, P = self.root, self.params
         p = [root[:, j] for j in range(0, 3)]
@@ -326,11 +367,14 @@ class QuadStepOracle:
         inertia = [P[:, 1], P[:, 2], P[:, 3]]
         inv_i = [1.0 / P[:, 1], 1.0 / P[:, 2], 1.0 / P[:, 3]]
         arm, cz = P[:, 4], c(cfg["com_z"])
-        f0, f1, f2, f3 = force[:, 0], force[:, 1], force[:, 2], force[:, 3]
-        fz = ((f0 + f1) + f2) + f3
-        tau_b = [arm * (((f1 - f0) + f2) - f3),
-                 arm * (((f1 - f0) - f2) + f3),
-                 c(cfg["yaw_km"]) * (((f2 - f0) - f1) + f3)]
+        if wrench is not None:
+            fz, tau_b = wrench
+        else:
+            f0, f1, f2, f3 = force[:, 0], force[:, 1], force[:, 2], force[:, 3]
+            fz = ((f0 + f1) + f2) + f3
+            tau_b = [arm * (((f1 - f0) + f2) - f3),
+                     arm * (((f1 - f0) - f2) + f3),
+                     c(cfg["yaw_km"]) * (((f2 - f0) - f1) + f3)]
         R = quat_to_R(q)
         b3 = [R[0][2], R[1][2], R[2][2]]
         fw = [b3[j] * fz for j in range(3)]

@@ -104,22 +104,24 @@ def get_euler_xyz(q):
 
 
 class HuskyFollower:
-    """Waypoint state machine of landing.py:208-244,319-364 + a kinematic differential-drive vehicle.
+    """Waypoint state machine of landing.py:208-244,319-364 + a kinematic differential-drive vehicle (CPU twin of
+    ouzelum_b200/csrc/targets.cu).
 
     Reference randomness (torch.randint / torch.rand on the global generator) is replaced by the counter RNG:
     a (re)draw at global step t uses philox.draw(seed, env, t, P_HUSKY): traj = mulhi(r0, 3), scale = 0.8 + 0.4*u(r1),
-    direction = +1 if r2 & 1 else -1.  The initial draw uses t = 2^63 (never reached by the step counter)."""
+    direction = +1 if r2 & 1 else -1; a re-spawn uses P_HUSKY+1.  The initial draw uses t = 2^63."""
 
     INIT_STEP = 1 << 63
 
-    def __init__(self, n, seed=0, env_id_base=0, dt=0.01, dist_thresh=0.2):
+    def __init__(self, n, seed=0, env_id_base=0, dt=0.01, dist_thresh=0.2, x_offset=0.08, target_z=0.377,
+                 respawn_limit=5.0, tables=None):
         f = np.float32
         self.n, self.seed, self.dt, self.thresh = n, seed, f(dt), f(dist_thresh)
+        self.x_offset, self.target_z, self.respawn_limit = f(x_offset), f(target_z), f(respawn_limit)
         self.ids = np.arange(n, dtype=np.uint64) + np.uint64(env_id_base)
-        self.tables = landing_tables()
-        self.traj, self.scale, self.direction = self._draw(self.INIT_STEP)          # landing.py:210-212
-        self.index = np.zeros(n, dtype=np.int64)                                    # :213
-        self.target = np.zeros((n, 2), dtype=f)                                     # :209
+        self.tables = tables if tables is not None else landing_tables()
+        self.traj, self.s = self._draw(self.INIT_STEP)                              # landing.py:210-212
+        self.index = np.zeros(n, dtype=np.int32)                                    # :213
         self.pos = np.zeros((n, 2), dtype=f)
         self.heading = np.zeros(n, dtype=f)
         self.step_count = 0
@@ -127,37 +129,46 @@ class HuskyFollower:
     def _draw(self, t):
         r0, r1, r2, _ = px.draw(self.seed, self.ids, t, px.P_HUSKY)
         traj = px.mulhi(r0, 3).astype(np.int32)
-        scale = np.float32(0.8) + np.float32(1.2 - 0.8) * px.u01(r1)                 # landing.py:211 / :241
+        scale = np.float32(0.8) + np.float32(0.4) * px.u01(r1)                       # landing.py:211 / :241
         direction = np.where((r2 & np.uint32(1)) != 0, np.float32(1), np.float32(-1)).astype(np.float32)
-        return traj, scale, direction
+        return traj, (scale * direction).astype(np.float32)
 
     def _lookup(self):
         out = np.zeros((self.n, 2), dtype=np.float32)
         for k, tab in enumerate(self.tables):
             m = self.traj == k
-            out[m] = tab[np.minimum(self.index[m], len(tab) - 1)]
-        return out * (self.scale * self.direction)[:, None]
+            out[m] = np.asarray(tab, dtype=np.float32)[np.minimum(self.index[m], len(tab) - 1)]
+        return out * self.s[:, None]
 
-    def step(self):
-        """One set_husky_actions (landing.py:319-364) + unicycle integration.  Returns wheel speeds [N,4]."""
+    def step(self, reset=None):
+        """One set_husky_actions (landing.py:319-364) + unicycle integration.  Returns (wheels [N,4], target3 [N,3])."""
         f = np.float32
-        self.target = self._lookup()                                               # :326-338
-        d = self.target - self.pos
-        dist = np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2)                                 # :339
-        self.index = self.index + (dist < self.thresh)                              # :342-343
+        if reset is not None:                                                      # landing.py:263-270
+            far = (np.asarray(reset) != 0) & ((np.abs(self.pos[:, 0]) > self.respawn_limit) |
+                                              (np.abs(self.pos[:, 1]) > self.respawn_limit))
+            r0, r1, _, _ = px.draw(self.seed, self.ids, self.step_count, px.P_HUSKY + 1)
+            nx, ny = f(3.0) * px.u01(r0) + f(-1.5), f(3.0) * px.u01(r1) + f(-1.5)
+            self.pos[:, 0] = np.where(far, nx, self.pos[:, 0])
+            self.pos[:, 1] = np.where(far, ny, self.pos[:, 1])
+            self.heading = np.where(far, f(0), self.heading)
+        tgt = self._lookup()                                                       # :326-338
+        d = tgt - self.pos
+        dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])                       # :339
+        self.index = (self.index + (dist < self.thresh)).astype(np.int32)           # :342-343
         done = (self.index == NUM_WAYPOINTS) | ((self.traj == 2) & (self.index > 3))   # :235-238
-        traj, scale, direction = self._draw(self.step_count)
-        self.traj = np.where(done, traj, self.traj)
-        self.scale = np.where(done, scale, self.scale)
-        self.direction = np.where(done, direction, self.direction)
-        self.index = np.where(done, 0, self.index)
-        self.target = self._lookup()                                               # :349-358
-        wheels = differential_drive(self.pos, self.target, self.heading, (3.0, 1000))   # :362
-        # kinematic unicycle (replaces the PhysX Husky): v = r (wr + wl)/2, yaw rate = r (wr - wl)/b... sign per controllers.py:31-32
+        traj, s = self._draw(self.step_count)
+        self.traj = np.where(done, traj, self.traj).astype(np.int32)
+        self.s = np.where(done, s, self.s).astype(f)
+        self.index = np.where(done, 0, self.index).astype(np.int32)
+        tgt = self._lookup()                                                       # :349-358
+        wheels = differential_drive(self.pos, tgt, self.heading, (3.0, 1000))       # :362
         right, left = wheels[:, 0], wheels[:, 1]
         v = f(WHEEL_RADIUS) * (right + left) * f(0.5)
         wz = f(WHEEL_RADIUS) * (left - right) / f(WHEEL_BASE)
-        self.pos = self.pos + np.stack([np.cos(self.heading), np.sin(self.heading)], -1) * (v * self.dt)[:, None]
-        self.heading = (self.heading + wz * self.dt).astype(f)
+        self.pos = (self.pos + np.stack([np.cos(self.heading), np.sin(self.heading)], -1) * (v * self.dt)[:, None]).astype(f)
+        h = self.heading + wz * self.dt
+        two_pi = f(2.0) * f(np.pi)
+        self.heading = (h - two_pi * np.floor(h / two_pi)).astype(f)
         self.step_count += 1
-        return wheels
+        target3 = np.stack([self.pos[:, 0] + self.x_offset, self.pos[:, 1], np.full(self.n, self.target_z, f)], -1).astype(f)
+        return wheels, target3

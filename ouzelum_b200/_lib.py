@@ -30,7 +30,7 @@ class OzlCfg(C.Structure):
         ("fault_mode", C.c_int32), ("fault_eff_lo", C.c_float), ("fault_eff_range", C.c_float),
         ("dr_enable", C.c_int32), ("dr_lo", C.c_float), ("dr_range", C.c_float),
         ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float), ("noise_sigma", C.c_float),
-        ("collect_metrics", C.c_int32), ("reserved1", C.c_int32),
+        ("collect_metrics", C.c_int32), ("plate_enable", C.c_int32), ("plate_z", C.c_float), ("plate_radius", C.c_float), ("land_cutoff", C.c_float),
     ]
 
     def to_dict(self):
@@ -65,15 +65,29 @@ class OzlPvArgs(C.Structure):
     ]
 
 
+class OzlHuskyArgs(C.Structure):
+    """Mirror of `struct ozl_husky_args` (include/ouzelum_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64), ("pose4", C.c_void_p), ("idx2", C.c_void_p), ("tables204x2", C.c_void_p), ("reset", C.c_void_p),
+        ("wheels4", C.c_void_p), ("target3", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("env_id_base", C.c_int64), ("dt", C.c_float), ("dist_thresh", C.c_float), ("kp_lin", C.c_float),
+        ("kp_ang", C.c_float), ("ang_thresh", C.c_float), ("x_offset", C.c_float), ("target_z", C.c_float),
+        ("respawn_limit", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ozl_abi_version": (C.c_int, []),
+    "ozl_cfg_size": (C.c_int, []),
     "ozl_last_error": (C.c_char_p, []),
     "ozl_cfg_default": (C.c_int, [C.POINTER(OzlCfg), C.c_int64]),
     "ozl_create": (C.c_int, [C.POINTER(OzlCfg), C.c_int, C.POINTER(_P)]),
     "ozl_destroy": (C.c_int, [_P]),
     "ozl_reset_all": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_step": (C.c_int, [_P] * 9),
+    "ozl_step_tracking": (C.c_int, [_P] * 10),
+    "ozl_step_wrench": (C.c_int, [_P] * 10),
     "ozl_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "ozl_get_state": (C.c_int, [_P] * 6),
     "ozl_set_state": (C.c_int, [_P] * 6),
@@ -83,6 +97,7 @@ _SIGS = {
     "ozl_set_step_count": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_metrics_read": (C.c_int, [_P, _P, C.c_int32, _P]),
     "ozl_lee_control": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_float), _P, _P, _P]),
+    "ozl_lee_wrench": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_float), C.c_float, _P, _P]),
     "ozl_pv_init": (C.c_int, [C.c_int64, _P, _P, _P]),
     "ozl_pv_reset": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
     "ozl_pv_step": (C.c_int, [C.POINTER(OzlPvArgs), _P]),
@@ -91,6 +106,8 @@ _SIGS = {
     "ozl_ekf_update": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P]),
     "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int32, _P, _P, _P]),
+    "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
+    "ozl_husky_step": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
 }
 
@@ -108,6 +125,9 @@ def _load():
     v = lib.ozl_abi_version()
     if v != OZL_ABI_VERSION:
         raise RuntimeError(f"ouzelum_b200: library ABI {v} != binding ABI {OZL_ABI_VERSION}; rebuild")
+    if lib.ozl_cfg_size() != C.sizeof(OzlCfg):
+        raise RuntimeError(f"ouzelum_b200: struct ozl_cfg is {lib.ozl_cfg_size()} bytes in the library but "
+                           f"{C.sizeof(OzlCfg)} in the binding; rebuild")
     return lib
 
 

@@ -1,4 +1,5 @@
-"""Build libouzelum_b200.so in-tree with nvcc for sm_100a (B200).  `python -m ouzelum_b200.build`.
+"""Build libouzelum_b200.so in-tree with nvcc for sm_100a (B200).  `python ouzelum_b200/build.py [--force] [-v]`
+(run it as a script: importing the package first would try to load the library being built).
 
 Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   Blackwell-only SASS (no PTX fallback for other archs)

@@ -25,6 +25,10 @@ _TASKS = {
                         "clipObservations": 5.0, "clipActions": 1.0, "enableCameraSensors": False},
                 "sim": _SIM, "task": {"randomize": False}},
 }
+# cfg/task/{Lando,Landing,Landed,LeeLanded}.yaml differ from Ouzelum.yaml only in `name`
+for _n in ("Lando", "Landing", "Landed", "LeeLanded"):
+    _TASKS[_n] = copy.deepcopy(_TASKS["Ouzelum"])
+    _TASKS[_n]["name"] = _n
 
 
 def task_names():

@@ -41,3 +41,14 @@ class Controller:
         check(lib.ozl_lee_control(self.mode, n, st.data_ptr(), cmd.data_ptr(), self._gains, thrust.data_ptr(),
                                   torque.data_ptr(), torch.cuda.current_stream().cuda_stream), ValueError)
         return thrust, torque
+
+    def wrench(self, robot_state, command_actions, thrust_scale, out=None):
+        """(thrust_scale * thrust, torque) packed as [N,4] -- the body wrench of tasks/lee_landed.py:313-314."""
+        st = robot_state.to(dtype=torch.float32).contiguous()
+        cmd = command_actions.to(dtype=torch.float32).contiguous()
+        n = st.shape[0]
+        if out is None:
+            out = torch.empty(n, 4, dtype=torch.float32, device=st.device)
+        check(lib.ozl_lee_wrench(self.mode, n, st.data_ptr(), cmd.data_ptr(), self._gains, float(thrust_scale),
+                                 out.data_ptr(), torch.cuda.current_stream().cuda_stream), ValueError)
+        return out

@@ -11,7 +11,7 @@ static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / 
 // ------------------------------------------------------------------------------------------------ K4
 __global__ void __launch_bounds__(128)
 lee_control_kernel(int mode, int64_t n, const float* __restrict__ state13, const float* __restrict__ cmd4, const LeeGains g,
-                   float* __restrict__ thrust, float* __restrict__ torque3) {
+                   float* __restrict__ thrust, float* __restrict__ torque3, float4* __restrict__ wrench4, float thrust_scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* s = state13 + i * 13;
@@ -20,8 +20,10 @@ lee_control_kernel(int mode, int64_t n, const float* __restrict__ state13, const
     const float cmd[4] = {c4.x * g.scale[0], c4.y * g.scale[1], c4.z * g.scale[2], c4.w * g.scale[3]};   // controller.py:47
     float th, tq[3];
     lee_control(mode, p, q, v, w, cmd, g, th, tq);
-    thrust[i] = th;
-    torque3[i * 3 + 0] = tq[0]; torque3[i * 3 + 1] = tq[1]; torque3[i * 3 + 2] = tq[2];
+    if (thrust) thrust[i] = th;
+    if (torque3) { torque3[i * 3 + 0] = tq[0]; torque3[i * 3 + 1] = tq[1]; torque3[i * 3 + 2] = tq[2]; }
+    // forces[:,0,2] = mg * thrust ; torques[:,0] = torque   (lee_landed.py:313-314, ekf_lee_landed.py:504-505)
+    if (wrench4) wrench4[i] = make_float4(thrust_scale * th, tq[0], tq[1], tq[2]);
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -205,7 +207,20 @@ extern "C" int ozl_lee_control(int32_t mode, int64_t n, const float* state13, co
     LeeGains g;
     for (int k = 0; k < 3; ++k) { g.kP[k] = gains16[k]; g.kV[k] = gains16[3 + k]; g.kR[k] = gains16[6 + k]; g.kO[k] = gains16[9 + k]; }
     for (int k = 0; k < 4; ++k) g.scale[k] = gains16[12 + k];
-    lee_control_kernel<<<nblk(n, 128), 128, 0, st>>>(mode, n, state13, cmd4, g, thrust, torque3);
+    lee_control_kernel<<<nblk(n, 128), 128, 0, st>>>(mode, n, state13, cmd4, g, thrust, torque3, nullptr, 0.0f);
+    return check_cuda(cudaGetLastError(), "lee_control_kernel");
+}
+
+extern "C" int ozl_lee_wrench(int32_t mode, int64_t n, const float* state13, const float* cmd4, const float* gains16,
+                              float thrust_scale, float* wrench4, void* stream) {
+    OZL_N_CHECK("ozl_lee_wrench");
+    if (mode < 0 || mode > 2) return set_error("Invalid controller name: mode %d (0 position, 1 velocity, 2 attitude)", mode);
+    if (!state13 || !cmd4 || !gains16 || !wrench4) return set_error("ozl_lee_wrench: NULL buffer");
+    if (((uintptr_t)cmd4 & 15) || ((uintptr_t)wrench4 & 15)) return set_error("ozl_lee_wrench: cmd4/wrench4 must be 16-byte aligned");
+    LeeGains g;
+    for (int k = 0; k < 3; ++k) { g.kP[k] = gains16[k]; g.kV[k] = gains16[3 + k]; g.kR[k] = gains16[6 + k]; g.kO[k] = gains16[9 + k]; }
+    for (int k = 0; k < 4; ++k) g.scale[k] = gains16[12 + k];
+    lee_control_kernel<<<nblk(n, 128), 128, 0, st>>>(mode, n, state13, cmd4, g, nullptr, nullptr, (float4*)wrench4, thrust_scale);
     return check_cuda(cudaGetLastError(), "lee_control_kernel");
 }
 

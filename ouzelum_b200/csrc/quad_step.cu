@@ -82,7 +82,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // into the block's slot.  Then the last block to finish (ticket) advances the step counter.
 template <int BLOCK>
 __device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl, bool valid, const StepOut& o,
-                                               uint64_t step, uint32_t step_inc, double (*s_m)[10]) {
+                                               uint64_t step, uint32_t step_inc, double (*s_m)[11]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (c.collect_metrics) {
         const unsigned full = 0xffffffffu;
@@ -97,17 +97,18 @@ __device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl
         const int n_cz = __popc(__ballot_sync(full, valid && o.crash_z));
         const int n_fa = __popc(__ballot_sync(full, valid && o.fault_active));
         const int n_rs = __popc(__ballot_sync(full, valid && o.did_reset));
+        const int n_ld = __popc(__ballot_sync(full, valid && o.landed_episode));
         if (lane == 0) {
             s_m[warp][0] = srew; s_m[warp][1] = sret; s_m[warp][2] = n_valid; s_m[warp][3] = n_done;
             s_m[warp][4] = slen; s_m[warp][5] = n_to; s_m[warp][6] = n_cd; s_m[warp][7] = n_cz;
-            s_m[warp][8] = n_fa; s_m[warp][9] = n_rs;
+            s_m[warp][8] = n_fa; s_m[warp][9] = n_rs; s_m[warp][10] = n_ld;
         }
         __syncthreads();
-        if (threadIdx.x < 10) {
+        if (threadIdx.x < 11) {
             double v = 0.0;
 #pragma unroll
             for (int wv = 0; wv < BLOCK / 32; ++wv) v += s_m[wv][threadIdx.x];
-            const int idx = threadIdx.x < 2 ? threadIdx.x : threadIdx.x + 6;   // sums at [0,1], counts at [8..15]
+            const int idx = threadIdx.x < 2 ? threadIdx.x : (threadIdx.x == 10 ? 2 : threadIdx.x + 6);   // sums [0,1], landed [2], counts [8..15]
             if (v != 0.0) atomicAdd(pl.metrics + (blockIdx.x % kMetricSlots) * kMetricStride + idx, v);
         }
     }
@@ -135,9 +136,10 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
 quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
-                 uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out) {
+                 uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
+                 const int act_mode) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
-    __shared__ double s_m[BLOCK / 32][10];
+    __shared__ double s_m[BLOCK / 32][11];
 
     const int64_t base = (int64_t)blockIdx.x * BLOCK;
     const int64_t i = base + threadIdx.x;
@@ -146,7 +148,7 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
 
     StepOut o;
     o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
-    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = false;
+    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
 
     if (valid) {
         // all loads issued up front: 9 x 128-bit + 2 x 64-bit per env in flight
@@ -157,6 +159,10 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         const bool rst = reset[i] != 0;
         Env e;
         unpack(L, e);
+        float tnew[3];
+        if (target_in) {     // externally driven target (landing family: target rides on the ground vehicle, landing.py:373-374)
+            tnew[0] = target_in[i * 3]; tnew[1] = target_in[i * 3 + 1]; tnew[2] = target_in[i * 3 + 2];
+        }
         const float act[4] = {a4.x, a4.y, a4.z, a4.w};
         const uint32_t genv = c.env_id_base + (uint32_t)i;
 #ifdef OZL_EXPERIMENT_NO_COMPUTE   // memory-system ceiling experiment only (never shipped)
@@ -164,12 +170,12 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         o.obs[12] = e.T[3] + e.eff + e.mass + __uint_as_float(e.fault);
         o.rew = e.ep_ret; o.prog = prog + 1; o.reset = rst;
 #else
-        env_step(e, act, prog, rst, genv, step, c, o);
+        env_step(e, act, prog, rst, genv, step, c, o, act_mode, target_in ? tnew : nullptr);
         obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
 #endif
 
         store_dynamic(pl, i, e);
-        if (o.static_dirty) store_static(pl, i, e);
+        if (o.static_dirty || target_in) store_static(pl, i, e);
         rew[i] = o.rew;
         reset[i] = o.reset ? 1 : 0;
         progress[i] = o.prog;
@@ -216,13 +222,13 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 quad_rollout_kernel(const DevCfg c, const Planes pl, int K, float* __restrict__ obs, float* __restrict__ rew,
                     int64_t* __restrict__ reset, int64_t* __restrict__ progress) {
-    __shared__ double s_m[BLOCK / 32][10];
+    __shared__ double s_m[BLOCK / 32][11];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < c.num_envs;
     const uint64_t step0 = ld_relaxed(pl.ctrl);
     StepOut o;
     o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
-    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = false;
+    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
     Env e;
     int64_t prog = 0;
     bool rst = false, dirty = false;
@@ -336,7 +342,7 @@ __global__ void get_params_kernel(const Planes pl, int64_t n, float* params7, in
         float* p = params7 + i * 7;
         p[0] = e.mass; p[1] = e.ixx; p[2] = e.iyy; p[3] = e.izz; p[4] = e.arm; p[5] = e.ks; p[6] = e.eff;
     }
-    if (fault2) { fault2[i * 2] = (int32_t)(e.fault & 3u); fault2[i * 2 + 1] = (int32_t)(e.fault >> 2); }
+    if (fault2) { fault2[i * 2] = (int32_t)(e.fault & 3u); fault2[i * 2 + 1] = (int32_t)((e.fault & ~LANDED_BIT) >> 2); }
 }
 
 __global__ void set_params_kernel(const Planes pl, int64_t n, const float* params7, const int32_t* fault2) {
@@ -350,7 +356,7 @@ __global__ void set_params_kernel(const Planes pl, int64_t n, const float* param
         const float* p = params7 + i * 7;
         e.mass = p[0]; e.inv_m = 1.0f / p[0]; e.ixx = p[1]; e.iyy = p[2]; e.izz = p[3]; e.arm = p[4]; e.ks = p[5]; e.eff = p[6];
     }
-    if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | ((uint32_t)fault2[i * 2 + 1] << 2);
+    if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | (((uint32_t)fault2[i * 2 + 1] & FAULT_NEVER) << 2) | (e.fault & LANDED_BIT);
     store_static(pl, i, e);
 }
 
@@ -419,6 +425,9 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
     d.h = (float)h;
     d.hh = (float)(0.5 * h);
     d.fault_eff_lo = c.fault_eff_lo; d.fault_eff_range = c.fault_eff_range;
+    d.land_cutoff = c.land_cutoff;
+    d.plate_enable = c.plate_enable; d.plate_z = c.plate_z;
+    d.plate_r2 = (float)((double)c.plate_radius * (double)c.plate_radius);
     d.dr_lo = c.dr_lo; d.dr_range = c.dr_range;
     d.flicker_p = (c.pomdp_mode == OZL_POMDP_FLICKER_NOISE) ? 0.1f : c.pomdp_prob;      // POMDP.py:16-18
     const float lo = (float)(1.0 - (double)c.noise_sigma), hi = (float)(1.0 + (double)c.noise_sigma);
@@ -439,6 +448,7 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
 }
 
 extern "C" int ozl_abi_version(void) { return OZL_ABI_VERSION; }
+extern "C" int ozl_cfg_size(void) { return (int)sizeof(ozl_cfg); }
 extern "C" const char* ozl_last_error(void) { return g_err; }
 
 extern "C" int ozl_cfg_default(ozl_cfg* c, int64_t num_envs) {
@@ -477,6 +487,7 @@ extern "C" int ozl_cfg_default(ozl_cfg* c, int64_t num_envs) {
     c->fault_eff_lo = 0.0f; c->fault_eff_range = 0.5f;
     c->dr_lo = 0.8f; c->dr_range = (float)(1.2 - 0.8);
     c->collect_metrics = 1;
+    c->plate_enable = 0; c->plate_z = 0.377f; c->plate_radius = 0.35f; c->land_cutoff = 0.0f;
     return 0;
 }
 
@@ -489,7 +500,7 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
         return set_error("ozl_create: cfg.abi_version %d != library %d", cfg->abi_version, OZL_ABI_VERSION);
     if (cfg->num_envs <= 0 || cfg->num_envs > 0x7FFFFFFFll) return set_error("ozl_create: num_envs out of range");
     if (cfg->substeps <= 0 || cfg->control_freq_inv <= 0) return set_error("ozl_create: substeps/control_freq_inv must be > 0");
-    if (cfg->max_episode_length <= 1 || cfg->max_episode_length >= (1 << 29))
+    if (cfg->max_episode_length <= 1 || cfg->max_episode_length >= (1 << 28))
         return set_error("ozl_create: max_episode_length out of range");
     if (cfg->target_period <= 0) return set_error("ozl_create: target_period must be > 0");
     if (cfg->pomdp_mode < 0 || cfg->pomdp_mode > 3) return set_error("ozl_create: unknown pomdp_mode %d", cfg->pomdp_mode);
@@ -555,14 +566,31 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 // Block size: 128 threads keeps >= 1 block on every SM down to ~19k envs and lets 16k-env launches use 128 SMs.
 constexpr int kStepBlock = OZL_STEP_BLOCK;
 
+static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
+                       int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who) {
+    if (!env) return set_error("%s: env is NULL", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!actions || !obs || !rew || !reset || !progress) return set_error("%s: NULL buffer", who);
+    if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("%s: actions/obs must be 16-byte aligned", who);
+    quad_step_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
+        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode);
+    return check_cuda(cudaGetLastError(), "quad_step_kernel");
+}
+
 extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
                         uint8_t* timeout, float* ep_ret, void* stream) {
-    OZL_ENV_CHECK("ozl_step");
-    if (!actions || !obs || !rew || !reset || !progress) return set_error("ozl_step: NULL buffer");
-    if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("ozl_step: actions/obs must be 16-byte aligned");
-    quad_step_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
-        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret);
-    return check_cuda(cudaGetLastError(), "quad_step_kernel");
+    return launch_step(env, actions, nullptr, ACT_ROTORS, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step");
+}
+
+extern "C" int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,
+                                 int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    if (!target3) return set_error("ozl_step_tracking: target3 is NULL");
+    return launch_step(env, actions, target3, ACT_ROTORS, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step_tracking");
+}
+
+extern "C" int ozl_step_wrench(ozl_env* env, const float* wrench4, const float* target3, float* obs, float* rew,
+                               int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    return launch_step(env, wrench4, target3, ACT_WRENCH, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step_wrench");
 }
 
 extern "C" int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int64_t* reset, int64_t* progress, void* stream) {

@@ -50,6 +50,16 @@ class QuadSim:
         check(lib.ozl_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(), reset.data_ptr(),
                            progress.data_ptr(), ptr(timeout), ptr(ep_ret), _stream()))
 
+    def step_tracking(self, actions, target, obs, rew, reset, progress, timeout=None, ep_ret=None):
+        """ozl_step_tracking: the target [N,3] is supplied by the caller (landing family)."""
+        check(lib.ozl_step_tracking(self._h, actions.data_ptr(), target.data_ptr(), obs.data_ptr(), rew.data_ptr(),
+                                    reset.data_ptr(), progress.data_ptr(), ptr(timeout), ptr(ep_ret), _stream()))
+
+    def step_wrench(self, wrench, target, obs, rew, reset, progress, timeout=None, ep_ret=None):
+        """ozl_step_wrench: actuation by a body wrench [N,4] = (fz, tx, ty, tz); target may be None."""
+        check(lib.ozl_step_wrench(self._h, wrench.data_ptr(), ptr(target), obs.data_ptr(), rew.data_ptr(),
+                                  reset.data_ptr(), progress.data_ptr(), ptr(timeout), ptr(ep_ret), _stream()))
+
     def rollout(self, k, obs, rew, reset, progress):
         check(lib.ozl_rollout(self._h, int(k), obs.data_ptr(), rew.data_ptr(), reset.data_ptr(), progress.data_ptr(),
                               _stream()))
@@ -115,6 +125,6 @@ class QuadSim:
         return out
 
 
-METRIC_NAMES = ("sum_reward", "sum_episode_return", None, None, None, None, None, None,
+METRIC_NAMES = ("sum_reward", "sum_episode_return", "landed_episodes", None, None, None, None, None,
                 "env_steps", "episodes", "sum_episode_length", "timeouts", "crash_dist", "crash_z",
                 "fault_active_steps", "resets")

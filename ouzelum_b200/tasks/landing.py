@@ -1,0 +1,85 @@
+"""Landing-family x500 tasks: the target rides on a ground vehicle.
+
+Mirrors isaacgymenvs/tasks/lando.py, landing.py and landed.py.  All three share Ouzelum's pre/post-physics code except
+  * target source: `target.xy = husky.xy; target.x += 0.08; target.z = 0.377` every step (landing.py:76,373-374)
+  * reward: die when z < 0.3 instead of 0.5 (landing.py:447)
+  * Landing: the Husky follows lemniscate / circle / square waypoints (landing.py:108-112,208-244,319-364)
+  * Landed: evaluation variant -- observation through the sensor-fault model env-side (landed.py:62,340), landing
+    detector that cuts thrust within 0.2 m of the target (landed.py:288-295), landing counter (landed.py:265-271)
+One step = one `ozl_husky_step` launch (vehicle + target) followed by one `ozl_step_tracking` launch.
+The PhysX Husky and the leg/plate contact are replaced by a kinematic unicycle and an inelastic plate.
+"""
+import torch
+
+from ..trajectories import HuskyFollower
+from .ouzelum import X500Task, x500_cfg_from_task
+
+TARGET_Z = 0.377          # landing.py:76
+TOP_PLATE_X_SHIFT = 0.08  # landing.py:374
+
+
+class _VehicleTargetTask(X500Task):
+    die_z = 0.3
+    x_offset = TOP_PLATE_X_SHIFT
+    vehicle_moves = True
+    land_cutoff = 0.0
+
+    def _native_cfg(self):
+        return x500_cfg_from_task(self.cfg, self.num_envs, target_fixed=1, die_z=self.die_z, plate_enable=1,
+                                  plate_z=TARGET_Z, plate_radius=0.35, land_cutoff=self.land_cutoff)
+
+    def create_sim(self):
+        super().create_sim()
+        env = self.cfg["env"]
+        self.husky = HuskyFollower(self.num_envs, self.device, seed=int(env.get("seed", 0)),
+                                   env_id_base=int(env.get("envIdBase", 0)), dt=float(self.cfg["sim"]["dt"]),
+                                   x_offset=self.x_offset, target_z=TARGET_Z, env_spacing=float(env.get("envSpacing", 2.5)))
+        # target_root_positions starts at (0,0,0.377) (landing.py:75-76)
+        t0 = torch.zeros(self.num_envs, 3, device=self.device)
+        t0[:, 2] = TARGET_Z
+        self.sim.set_state(target=t0)
+        self._target = self.husky.target
+
+    def _launch(self, actions):
+        if self.vehicle_moves:
+            self._target = self.husky.step(self.reset_buf)
+        self.sim.step_tracking(actions, self._target, self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf,
+                               self._timeout_u8, self.episode_return_buf)
+
+    @property
+    def husky_positions(self):
+        return self.husky.husky_positions
+
+
+class Lando(_VehicleTargetTask):
+    """isaacgymenvs/tasks/lando.py: the Husky is driven with constant opposing wheel targets (lando.py, create_envs:
+    set_actor_dof_velocity_targets [10,-20,20,-10]) -- it turns on the spot, so the target stays at the spawn point."""
+    vehicle_moves = False
+
+
+class Landing(_VehicleTargetTask):
+    """isaacgymenvs/tasks/landing.py: waypoint-following Husky; `extras["reset_ids"]` as at landing.py:379."""
+
+    def step(self, actions):
+        out = super().step(actions)
+        return out
+
+    def get_reset_ids(self):
+        return self.reset_buf.nonzero(as_tuple=False).squeeze(-1)       # landing.py:283-284 (host sync; only when asked)
+
+
+class Landed(_VehicleTargetTask):
+    """isaacgymenvs/tasks/landed.py: evaluation variant (the reference supports num_envs == 1 only, landed.py:290)."""
+    land_cutoff = 0.2                                                  # landed.py:290
+
+    def __init__(self, cfg, *a, **k):
+        cfg["env"].setdefault("POMDP", "flicker")                      # landed.py:62: POMDPWrapper(pomdp='flicker', ...)
+        if cfg["env"].get("POMDP") in (None, "none"):
+            cfg["env"]["POMDP"] = "flicker"
+        cfg["env"].setdefault("pomdp_prob", 0.01)
+        super().__init__(cfg, *a, **k)
+
+    @property
+    def landings(self):
+        """Episodes that ended after the vehicle was reached (the reference writes this to metrics/<pomdp>_<p>.txt)."""
+        return int(self.sim.metrics()[2].item())

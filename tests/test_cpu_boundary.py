@@ -1,0 +1,133 @@
+"""CPU-only checks of the boundary and host logic: the C-ABI library builds, loads and exports every symbol that
+include/ouzelum_b200.h declares (no compute calls -- there is no GPU here), struct mirrors agree with the C defaults,
+the counter RNG passes the Random123 known-answer vectors, and the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ozl_build", os.path.join(ROOT, "ouzelum_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    build.build()                      # no-op when the in-tree .so is newer than its sources
+    from ouzelum_b200 import _lib
+    return _lib
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ouzelum_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ozl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_symbols()
+    assert len(names) >= 24, names
+    so = ctypes.CDLL(lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(so, n)]
+    assert not missing, f"declared in include/ouzelum_b200.h but not exported: {missing}"
+    bound = set(lib._SIGS)
+    assert set(names) == bound, f"ctypes binding and header disagree: {set(names) ^ bound}"
+    assert lib.lib.ozl_abi_version() == lib.OZL_ABI_VERSION
+
+
+def test_library_is_sm100a_only_and_uses_bulk_copy(lib):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass                      # TMA bulk store of the observation tile (Blackwell/Hopper async copy engine)
+    assert "quad_step_kernel" in sass
+
+
+def test_cfg_defaults_match_reference_yaml_and_urdf(lib):
+    from ouzelum_b200 import x500
+    c = lib.default_cfg(4096).to_dict()
+    assert c["max_episode_length"] == 2000 and c["target_period"] == 500 and c["substeps"] == 2      # Ouzelum.yaml:10,21
+    assert c["dt"] == np.float32(0.01) and c["gravity_z"] == np.float32(-9.81)
+    assert c["clip_actions"] == 1.0 and c["clip_obs"] == 5.0 and c["thrust_rate"] == 20.0 and c["thrust_max"] == 2000.0
+    assert c["die_dist"] == 8.0 and c["die_z"] == 0.5 and c["up_coef"] == 5.0
+    assert c["spawn_lo"] == tuple(np.float32([-1.5, -1.5, -0.2])) and c["spawn_range"] == tuple(np.float32([3.0, 3.0, 1.7]))
+    for k in ("mass", "ixx", "iyy", "izz", "arm", "com_z", "max_angvel"):
+        assert c[k] == float(np.float32(getattr(x500, k.upper()))), k
+    assert abs(x500.MASS - 2.0643077) < 1e-6 and abs(x500.COM_Z - 0.0093457) < 1e-6
+    assert abs(x500.IXX - 0.029275) < 2e-6 and abs(x500.IZZ - 0.0440) < 1e-6
+    with pytest.raises(KeyError):
+        lib.default_cfg(8, no_such_field=1)
+
+
+def test_oracle_constants_agree_with_product(lib):
+    from oracle import x500 as ox
+    from oracle.quad_step import default_cfg
+    from ouzelum_b200 import x500
+    for k in ("MASS", "COM_Z", "IXX", "IYY", "IZZ", "ARM", "MAX_ANGVEL"):
+        assert abs(getattr(ox, k) - getattr(x500, k)) < 1e-15, k
+    o, c = default_cfg(64), lib.default_cfg(64).to_dict()
+    for k, v in c.items():
+        if k in ("collect_metrics",):
+            continue
+        ov = o[k]
+        if isinstance(v, tuple):
+            assert tuple(np.float32(ov)) == tuple(np.float32(v)), k
+        elif isinstance(v, float):
+            assert np.float32(ov) == np.float32(v), k
+        else:
+            assert ov == v, k
+
+
+def test_philox_known_answers():
+    from oracle.philox import philox4x32_10, u01, mulhi
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]                     # Random123 kat_vectors, philox4x32 10 rounds
+    for ctr, key, want in kat:
+        got = philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == want
+    r = np.array([0, 255, 256, 0xFFFFFFFF], dtype=np.uint32)
+    assert list(u01(r)) == [0.0, 0.0, 2.0 ** -24, 1.0 - 2.0 ** -24]
+    assert list(mulhi(r, 2000)) == [0, 0, 0, 1999]
+
+
+def test_product_refuses_to_run_without_cuda(lib):
+    import torch
+    import ouzelum_b200
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ouzelum_b200.make(0, "Ouzelum", 16, sim_device="cpu", rl_device="cpu")
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU"):
+        ouzelum_b200.make(0, "Ouzelum", 16)
+    with pytest.raises(KeyError):
+        ouzelum_b200.make(0, "NoSuchTask", 16)
+    from ouzelum_b200.controllers import Controller, control
+    with pytest.raises(RuntimeError):
+        Controller(control(), "cpu")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ouzelum_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_task_config_mirrors_yaml():
+    import ouzelum_b200
+    c = ouzelum_b200.task_config("Ouzelum", 123)
+    assert c["env"]["numEnvs"] == 123 and c["env"]["maxEpisodeLength"] == 2000 and c["sim"]["substeps"] == 2
+    assert c["env"]["clipObservations"] == 5.0 and c["task"]["randomize"] is False
+    from ouzelum_b200.spaces import Box
+    b = Box(np.ones(4) * -1.0, np.ones(4) * 1.0)
+    assert b.shape == (4,) and b.contains(b.sample())

@@ -1,0 +1,149 @@
+"""GPU tests of the task layer: VecTask surface of `make()`, the tracking / wrench step variants against the oracle,
+the waypoint-following vehicle (K5) against its oracle, and closed-loop behaviour of the classical tasks."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_make_returns_vectask_surface_and_steps():
+    import ouzelum_b200
+    n = 300
+    env = ouzelum_b200.make(seed=3, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, graphics_device_id=-1, headless=True)
+    assert env.num_envs == n and env.num_obs == 13 and env.num_acts == 4 and env.num_states == 0
+    assert env.observation_space.shape == (13,) and env.action_space.shape == (4,)
+    assert float(env.action_space.low.min()) == -1.0 and float(env.action_space.high.max()) == 1.0
+    assert env.max_episode_length == 2000 and env.control_freq_inv == 1 and env.device == DEV
+    # allocate_buffers contract (vec_task.py:254-277)
+    assert env.obs_buf.shape == (n, 13) and env.obs_buf.dtype == torch.float32
+    assert env.reset_buf.dtype == torch.int64 and bool((env.reset_buf == 1).all())
+    assert env.progress_buf.dtype == torch.int64 and env.rew_buf.shape == (n,) and env.timeout_buf.dtype == torch.bool
+    obs = env.reset()
+    assert set(obs) == {"obs"} and float(obs["obs"].abs().max()) == 0.0          # reset() returns the zero buffer, no simulation
+    a = env.zero_actions()
+    assert a.shape == (n, 4)
+    o, r, d, info = env.step(torch.rand(n, 4, device=DEV) * 2 - 1)
+    assert o["obs"].shape == (n, 13) and r.shape == (n,) and d.dtype == torch.int64 and "time_outs" in info
+    assert bool((env.progress_buf == 1).all()) and float(o["obs"].abs().max()) <= 5.0
+    assert env.root_states.shape == (n, 13) and env.thrusts.shape == (n, 4) and env.target_root_positions.shape == (n, 3)
+    # reset_idx / reset_done (vec_task.py:391-406)
+    env.reset_idx(torch.tensor([1, 5], device=DEV))
+    _, ids = env.reset_done()
+    assert set(ids.tolist()) >= {1, 5}
+    env.step(a)
+    assert int(env.progress_buf[1]) == 1 and int(env.progress_buf[0]) == 2
+    env.close()
+
+
+def test_cuda_graph_step_equals_plain_step():
+    import ouzelum_b200
+    n = 2048
+    mk = lambda g: ouzelum_b200.make(seed=5, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                     cfg=ouzelum_b200.task_config("Ouzelum", n, seed=5, useCudaGraph=g, rotorFault={"enable": True}))
+    e1, e2 = mk(False), mk(True)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    for t in range(40):
+        a = torch.rand(n, 4, device=DEV, generator=gen) * 2 - 1
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a.clone())
+        assert torch.equal(o1["obs"], o2["obs"]) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert e2._graph is not None and e1.sim.step_count == e2.sim.step_count == 40
+
+
+def _bufs(n):
+    return dict(obs=torch.zeros(n, 13, device=DEV), rew=torch.zeros(n, device=DEV),
+                reset=torch.ones(n, dtype=torch.int64, device=DEV), progress=torch.zeros(n, dtype=torch.int64, device=DEV),
+                timeout=torch.zeros(n, dtype=torch.uint8, device=DEV), ep_ret=torch.zeros(n, device=DEV))
+
+
+def test_tracking_and_wrench_steps_bit_exact_vs_oracle():
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+    from oracle.quad_step import QuadStepOracle
+    n = 700
+    cfg = _lib.default_cfg(n, seed=21, target_fixed=1, die_z=0.3, plate_enable=1, land_cutoff=0.4, max_episode_length=80)
+    sim, ora, b = QuadSim(cfg, DEV), QuadStepOracle(cfg.to_dict()), _bufs(n)
+    g = torch.Generator().manual_seed(4)
+    hover = float(np.float32(2.0643077 * 9.81))
+    for t in range(160):
+        tgt = torch.rand(n, 3, generator=g) * torch.tensor([3.0, 3.0, 0.0]) + torch.tensor([-1.5, -1.5, 0.377])
+        if t % 2 == 0:
+            a = (torch.rand(n, 4, generator=g) * 2 - 1) * 0.3
+            sim.step_tracking(a.to(DEV), tgt.to(DEV), b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+            ora.step(a, target_in=tgt)
+        else:
+            w = torch.cat([hover + torch.randn(n, 1, generator=g), torch.randn(n, 3, generator=g) * 0.02], 1)
+            sim.step_wrench(w.to(DEV), tgt.to(DEV), b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+            ora.step(w, target_in=tgt, act_mode=1)
+        assert torch.equal(b["reset"].cpu(), ora.reset_buf), t
+        assert torch.equal(b["progress"].cpu(), ora.progress_buf), t
+        assert torch.equal(b["obs"].cpu(), ora.obs_buf), t
+        assert torch.equal(b["rew"].cpu(), ora.rew_buf), t
+        st = sim.get_state()
+        assert torch.equal(st["root"].cpu(), ora.root), t
+        assert torch.equal(st["target"].cpu(), ora.target), t
+    m = sim.metrics().cpu().numpy()
+    assert m[2] == ora.mlanded and ora.mlanded > 0, (m[2], ora.mlanded)       # landing counter (landed.py:265-271)
+    np.testing.assert_array_equal(m[8:16], ora.mcnt.astype(np.float64))
+
+
+def test_husky_follower_vs_oracle():
+    from ouzelum_b200.trajectories import HuskyFollower, landing_tables
+    from oracle.trajectories import HuskyFollower as Ora
+    n = 512
+    tabs = landing_tables("cpu").numpy()
+    hf = HuskyFollower(n, DEV, seed=8, env_id_base=40)
+    ora = Ora(n, seed=8, env_id_base=40, tables=(tabs[:100], tabs[100:200], tabs[200:204]))
+    assert np.array_equal(hf.idx[:, 0].cpu().numpy(), ora.traj) and set(ora.traj.tolist()) == {0, 1, 2}
+    np.testing.assert_array_equal(hf.pose[:, 3].cpu().numpy(), ora.s)
+    mism = 0
+    for t in range(400):
+        tgt = hf.step().cpu().numpy()
+        wheels, otgt = ora.step()
+        # same inputs each step: re-synchronise the oracle's continuous state, compare discrete state exactly
+        idx = hf.idx.cpu().numpy()
+        mism += int((idx[:, 1] != ora.index).sum() + (idx[:, 0] != ora.traj).sum())
+        np.testing.assert_allclose(hf.wheels.cpu().numpy(), wheels, rtol=2e-3, atol=2e-2)
+        np.testing.assert_allclose(tgt, otgt, rtol=1e-4, atol=2e-4)
+        pose = hf.pose.cpu().numpy()
+        ora.pos, ora.heading, ora.s = pose[:, 0:2].copy(), pose[:, 2].copy(), pose[:, 3].copy()
+        ora.index, ora.traj = idx[:, 1].copy(), idx[:, 0].copy()
+    assert mism <= 2, mism                       # a waypoint switch exactly at the 0.2 m threshold may flip by rounding
+    assert int(hf.idx[:, 1].max()) > 3           # vehicles do progress along their trajectories
+    assert float(hf.pose[:, 0:2].abs().max()) < 6.0
+
+
+def test_landing_family_tasks_run_and_track_vehicle():
+    import ouzelum_b200
+    n = 256
+    env = ouzelum_b200.make(seed=1, task="Landing", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    for t in range(50):
+        o, r, d, _ = env.step(torch.zeros(n, 4, device=DEV))
+    tgt = env.target_root_positions
+    hp = env.husky_positions
+    assert torch.allclose(tgt[:, 0], hp[:, 0] + 0.08, atol=1e-6) and torch.allclose(tgt[:, 1], hp[:, 1])     # landing.py:373-374
+    assert torch.allclose(tgt[:, 2], torch.full((n,), 0.377, device=DEV))
+    assert float(hp.abs().max()) > 0.01
+    lando = ouzelum_b200.make(seed=1, task="Lando", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    for t in range(5):
+        lando.step(torch.zeros(n, 4, device=DEV))
+    assert torch.allclose(lando.target_root_positions, torch.tensor([0.08, 0.0, 0.377], device=DEV).expand(n, 3))
+    assert int(lando.native_cfg.to_dict()["die_z"] * 10) == 3                    # z < 0.3 variant of the reward (landing.py:447)
+
+
+def test_lee_landed_closed_loop_reaches_hover_point():
+    """Controller + integrator in closed loop: the Lee position controller (gains of control_config.py) must fly the
+    x500 from its random spawn to (0,0,1) and hold it -- a physics sanity check of rows L, L', P together."""
+    import ouzelum_b200
+    n = 128
+    env = ouzelum_b200.make(seed=2, task="LeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    a = torch.zeros(n, 4, device=DEV)
+    for t in range(1500):
+        env.step(a)
+    root = env.root_states
+    dist = (root[:, 0:3] - torch.tensor([0.0, 0.0, 1.0], device=DEV)).norm(dim=1)
+    assert float(dist.median()) < 0.25, float(dist.median())
+    assert bool(env.landed_flag.any())
+    assert float(root[:, 10:13].abs().max()) < 1.0
