@@ -240,6 +240,33 @@ typedef struct ozl_husky_args {
 int ozl_husky_init(const ozl_husky_args* args, void* stream);
 int ozl_husky_step(const ozl_husky_args* args, void* stream);
 
+/* Stock Quadcopter hover task (BASELINE config 1): one fused step.  Replaces VecTask.step with the hooks of
+ * isaacgymenvs/tasks/quadcopter.py:280-330,359-418.  All state is caller-owned AoS device memory:
+ *   actions12 [n,12] in; root13 [n,13], dof_pos8 [n,8], dof_target8 [n,8], thrust4 [n,4] in/out;
+ *   obs21 [n,21], rew [n] out; reset [n] i64, progress [n] i64 in/out; timeout [n] u8 out or NULL.
+ * `step` is the caller-maintained step index (the RNG's time axis).  mass / inertia: the composite rigid body of the
+ * procedurally built vehicle (quadcopter.py:121-202), computed by the host binding. */
+typedef struct ozl_quadcopter_args {
+    int64_t n;
+    const float* actions12;
+    float* root13;
+    float* dof_pos8;
+    float* dof_target8;
+    float* thrust4;
+    float* obs21;
+    float* rew;
+    int64_t* reset;
+    int64_t* progress;
+    uint8_t* timeout;
+    uint64_t seed, step;
+    int64_t env_id_base;
+    int32_t max_episode_length;   /* 500   cfg/task/Quadcopter.yaml:10 */
+    int32_t substeps;             /* 2                                 */
+    float dt, gravity_z, clip_actions, clip_obs;
+    float mass, ixx, iyy, izz;
+} ozl_quadcopter_args;
+int ozl_quadcopter_step(const ozl_quadcopter_args* args, void* stream);
+
 const char* ozl_last_error(void);
 int ozl_abi_version(void);
 int ozl_cfg_size(void);            /* sizeof(ozl_cfg): lets a binding verify its struct mirror */

@@ -356,7 +356,7 @@ class QuadStepOracle:
         return self.obs_buf, self.rew_buf, self.reset_buf, self.timeout_buf
 
     # ------------------------------------------------------------------ rigid body
-    def _simulate(self, force, wrench=None):
+    def _simulate(self, force, wrench=None, body_force=None):
         cfg, c = self.cfg, self._c
         root, P = self.root, self.params
         p = [root[:, j] for j in range(0, 3)]
@@ -377,7 +377,7 @@ class QuadStepOracle:
                      c(cfg["yaw_km"]) * (((f2 - f0) - f1) + f3)]
         R = quat_to_R(q)
         b3 = [R[0][2], R[1][2], R[2][2]]
-        fw = [b3[j] * fz for j in range(3)]
+        fw = _matvec(R, body_force) if body_force is not None else [b3[j] * fz for j in range(3)]
         tau_w = _matvec(R, tau_b)
         # root (base-link origin) -> composite COM
         rc = [cz * b3[j] for j in range(3)]

@@ -76,6 +76,18 @@ class OzlHuskyArgs(C.Structure):
     ]
 
 
+class OzlQuadcopterArgs(C.Structure):
+    """Mirror of `struct ozl_quadcopter_args` (include/ouzelum_b200.h)."""
+    _fields_ = [
+        ("n", C.c_int64), ("actions12", C.c_void_p), ("root13", C.c_void_p), ("dof_pos8", C.c_void_p),
+        ("dof_target8", C.c_void_p), ("thrust4", C.c_void_p), ("obs21", C.c_void_p), ("rew", C.c_void_p),
+        ("reset", C.c_void_p), ("progress", C.c_void_p), ("timeout", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("env_id_base", C.c_int64), ("max_episode_length", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_float),
+        ("gravity_z", C.c_float), ("clip_actions", C.c_float), ("clip_obs", C.c_float), ("mass", C.c_float),
+        ("ixx", C.c_float), ("iyy", C.c_float), ("izz", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ozl_abi_version": (C.c_int, []),
@@ -108,6 +120,7 @@ _SIGS = {
                                         C.c_int32, _P, _P, _P]),
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_husky_step": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
+    "ozl_quadcopter_step": (C.c_int, [C.POINTER(OzlQuadcopterArgs), _P]),
     "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -31,6 +31,13 @@ for _n in ("Lando", "Landing", "Landed", "LeeLanded"):
     _TASKS[_n]["name"] = _n
 
 
+# cfg/task/Quadcopter.yaml
+_TASKS["Quadcopter"] = {"name": "Quadcopter", "physics_engine": "physx",
+                        "env": {"numEnvs": 8192, "envSpacing": 1.25, "maxEpisodeLength": 500, "enableDebugVis": False,
+                                "clipObservations": 5.0, "clipActions": 1.0, "enableCameraSensors": False},
+                        "sim": _SIM, "task": {"randomize": False}}
+
+
 def task_names():
     return sorted(_TASKS)
 

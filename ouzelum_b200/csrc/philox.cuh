@@ -11,6 +11,8 @@ enum : uint32_t {
     P_FAULT = 2,     // r0 -> rotor ; r1 -> onset ; r2 -> effectiveness
     P_DR0 = 3,       // mass, Ixx, Iyy, Izz scalings
     P_DR1 = 4,       // arm, thrust-scale scalings
+    P_QDOF0 = 5,     // Quadcopter task: initial DOF positions 0..3
+    P_QDOF1 = 6,     //                  initial DOF positions 4..7
     P_OBSNOISE = 8,  // +0..+3: 13 sensor-noise uniforms
     P_FLICKER = 12,  // global blackout draw (env word = GLOBAL_ENV)
     P_ACTION = 16,   // synthetic roll-out actions

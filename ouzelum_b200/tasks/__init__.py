@@ -2,6 +2,7 @@
 from .landing import Landed, Landing, Lando
 from .lee_landed import LeeLanded
 from .ouzelum import Ouzelum
+from .quadcopter import Quadcopter
 
 task_map = {
     "Ouzelum": Ouzelum,
@@ -9,4 +10,5 @@ task_map = {
     "Landing": Landing,
     "Landed": Landed,
     "LeeLanded": LeeLanded,
+    "Quadcopter": Quadcopter,
 }

@@ -147,3 +147,45 @@ def test_lee_landed_closed_loop_reaches_hover_point():
     assert float(dist.median()) < 0.25, float(dist.median())
     assert bool(env.landed_flag.any())
     assert float(root[:, 10:13].abs().max()) < 1.0
+
+
+def test_quadcopter_task_bit_exact_vs_oracle_config1():
+    """BASELINE config 1: Quadcopter hover, 256 envs, random actions U(-1,1) [256,12] from Generator(0)."""
+    import ouzelum_b200
+    from oracle.quadcopter import QuadcopterOracle, vehicle_constants
+    from ouzelum_b200.tasks.quadcopter import vehicle_constants as vc2
+    assert vehicle_constants() == vc2()
+    assert abs(vehicle_constants()["mass"] - 0.2516) < 1e-3
+    n = 256
+    env = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    assert env.num_obs == 21 and env.num_acts == 12 and env.max_episode_length == 500
+    ora = QuadcopterOracle(n, seed=0)
+    g = torch.Generator().manual_seed(0)
+    dones = 0
+    for t in range(300):
+        a = torch.rand(n, 12, generator=g) * 2 - 1
+        o, r, d, info = env.step(a.to(DEV))
+        ora.step(a)
+        assert torch.equal(d.cpu(), ora.reset_buf), t
+        assert torch.equal(env.progress_buf.cpu(), ora.progress_buf), t
+        assert torch.equal(o["obs"].cpu(), ora.obs_buf), f"obs t={t} max {(o['obs'].cpu()-ora.obs_buf).abs().max()}"
+        assert torch.equal(r.cpu(), ora.rew_buf), t
+        assert torch.equal(env.root_states.cpu(), ora.root), t
+        assert torch.equal(info["time_outs"].cpu(), ora.timeout_buf), t
+        dones += int(d.sum())
+    assert dones > 0
+    # hover: four equal thrusts of m g / 4 hold altitude
+    hover = vehicle_constants()["mass"] * 9.81 / 4
+    env.thrusts[:] = hover
+    env.root_states[:, 7:13] = 0
+    env.root_states[:, 3:7] = torch.tensor([0.0, 0.0, 0.0, 1.0], device=DEV)
+    env.dof_position_targets[:] = 0
+    env.dof_positions[:] = 0
+    env.reset_buf[:] = 0
+    env.progress_buf[:] = 1
+    z0 = env.root_states[:, 2].clone()
+    for _ in range(20):
+        env.step(torch.zeros(n, 12, device=DEV))
+    alive = env.progress_buf == 21                      # envs that were not re-spawned meanwhile (dist > 3 or z < 0.3)
+    assert int(alive.sum()) > n // 4
+    assert float((env.root_states[:, 2] - z0)[alive].abs().max()) < 1e-3
