@@ -118,6 +118,13 @@ int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, 
 int ozl_step_wrench(ozl_env* env, const float* wrench4, const float* target3, float* obs, float* rew,
                     int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
 
+/* Apply pending resets to the private state WITHOUT stepping: for envs with reset != 0 the spawn pose / target / fault
+ * schedule / randomised parameters are drawn exactly as the next ozl_step* will draw them again (the draws are pure
+ * functions of (seed, env, step counter), so re-applying is idempotent).  reset / progress buffers, metrics and the step
+ * counter are untouched.  Lets composite tasks see the post-reset state in their pre-physics code, as the reference does
+ * (reset_idx runs first in pre_physics_step, tasks/ekf_lee_landed.py:312-314, lee_landed.py:267-270). */
+int ozl_apply_resets(ozl_env* env, const int64_t* reset, void* stream);
+
 /* Mode-B throughput entry: K steps in ONE launch, state held in registers, actions a = 2u-1 drawn
  * in-kernel from the counter RNG; obs/rew are written for the LAST step only, reset/progress are
  * carried.  No reference counterpart (SURVEY 8d "mode B"). */
@@ -199,7 +206,17 @@ int ozl_pv_step(const ozl_pv_args* args, void* stream);                         
 int ozl_ekf_init(int64_t n, double* q4xN, double* P16xN, void* stream);                    /* q = (1,0,0,0), P = I4 (ahrs_ekf.py:995) */
 int ozl_ekf_set_q(int64_t n, double* q4xN, const float* quat_xyzw, const int64_t* flags, void* stream);   /* Q_state[flagged] = quat[[3,0,1,2]]; flags NULL = all */
 int ozl_ekf_update(int64_t n, double* q4xN, double* P16xN, const float* gyr3, const float* ang4, int32_t ang_xyzw,
-                   double Dt, double g_noise, void* stream);
+                   double Dt, double g_noise, float* q_wxyz_f32_out /* [n,4] or NULL */, void* stream);
+
+/* Glue kernels of EKFLeeLanded.pre_physics_step (isaacgymenvs/tasks/ekf_lee_landed.py:339-503).
+ * ozl_sensor_frontend: sensors16 [n,16] = accel(3)|gyr(3)|ang xyzw(4)|pos(3)|vel(3) from the true root state, through the
+ *   sensor-fault model when mode != 0 (:345-346,366-375,397-406); prev_linvel3 [n,3] is read then updated (:454).
+ * ozl_waypoint_command: carrot-waypoint logic and controller-input assembly (:458-503): waypoint3 [n,3] in/out,
+ *   est13 [n,13] = truth (warm-up) or [PV pos, true quat, PV vel, true angvel], cmd4 [n,4] = (waypoint, yaw 0). */
+int ozl_sensor_frontend(int64_t n, const float* root13, float* prev_linvel3, float* sensors16, float dt, int32_t mode,
+                        float pomdp_prob, uint64_t seed, uint64_t step, int64_t env_id_base, void* stream);
+int ozl_waypoint_command(int64_t n, const float* root13, const float* pv_x9xN, const float* target3, float* waypoint3,
+                         int32_t warmup, float* est13, float* cmd4, void* stream);
 
 /* Sensor-fault model on an [n,d] f32 array.  Replaces POMDPWrapper.observation (isaacgymenvs/utils/POMDP.py:23-42).
  * mode: OZL_POMDP_FLICKER / _NOISE / _FLICKER_NOISE (anything else: the reference's ValueError text).

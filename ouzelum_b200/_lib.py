@@ -115,7 +115,11 @@ _SIGS = {
     "ozl_pv_step": (C.c_int, [C.POINTER(OzlPvArgs), _P]),
     "ozl_ekf_init": (C.c_int, [C.c_int64, _P, _P, _P]),
     "ozl_ekf_set_q": (C.c_int, [C.c_int64, _P, _P, _P, _P]),
-    "ozl_ekf_update": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P]),
+    "ozl_ekf_update": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P]),
+    "ozl_sensor_frontend": (C.c_int, [C.c_int64, _P, _P, _P, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_uint64,
+                                      C.c_int64, _P]),
+    "ozl_waypoint_command": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "ozl_apply_resets": (C.c_int, [_P, _P, _P]),
     "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int32, _P, _P, _P]),
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),

@@ -48,7 +48,7 @@ class EKFBank:
         if P is not None:
             self._P.copy_(P.to(self.device, torch.float64).reshape(self.n, 16).t())
 
-    def update(self, gyr, ang, acc=None, ang_xyzw=False, check_norm=False):
+    def update(self, gyr, ang, acc=None, ang_xyzw=False, check_norm=False, q_f32_out=None):
         """EKF.update for every env: gyr [N,3] f32, ang [N,4] f32 (wxyz, or xyzw with ang_xyzw=True).  `acc` is accepted
         for signature parity and unused (it only feeds dead code on this branch).  Returns Q_state [N,4]."""
         if check_norm:                                                       # ahrs_ekf.py:1301-1302 (host sync: debug only)
@@ -58,5 +58,5 @@ class EKFBank:
         g = gyr.to(self.device, torch.float32).contiguous()
         a = ang.to(self.device, torch.float32).contiguous()
         check(lib.ozl_ekf_update(self.n, self._q.data_ptr(), self._P.data_ptr(), g.data_ptr(), a.data_ptr(),
-                                 1 if ang_xyzw else 0, float(self.Dt), self.g_noise, _s()))
+                                 1 if ang_xyzw else 0, float(self.Dt), self.g_noise, ptr(q_f32_out), _s()))
         return self.Q_state

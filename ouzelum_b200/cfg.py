@@ -31,6 +31,12 @@ for _n in ("Lando", "Landing", "Landed", "LeeLanded"):
     _TASKS[_n]["name"] = _n
 
 
+# cfg/task/EKFLeeLanded.yaml
+_TASKS["EKFLeeLanded"] = copy.deepcopy(_TASKS["Ouzelum"])
+_TASKS["EKFLeeLanded"]["name"] = "EKFLeeLanded"
+_TASKS["EKFLeeLanded"]["env"].update({"envSpacing": 5, "maxEpisodeLength": 700, "POMDP": "flicker", "pomdp_prob": 0.1,
+                                      "ConvergenceTime": 300, "attach_pos_sensor": True, "attach_vel_sensor": True,
+                                      "position_sensor_freq": 20, "velocity_sensor_freq": 75})
 # cfg/task/Quadcopter.yaml
 _TASKS["Quadcopter"] = {"name": "Quadcopter", "physics_engine": "physx",
                         "env": {"numEnvs": 8192, "envSpacing": 1.25, "maxEpisodeLength": 500, "enableDebugVis": False,

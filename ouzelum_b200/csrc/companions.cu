@@ -112,7 +112,8 @@ __global__ void pv_reset_kernel(int64_t n, float* x, const int64_t* flags, const
 // ------------------------------------------------------------------------------------------------ K2
 __global__ void __launch_bounds__(128)
 ekf_update_kernel(int64_t n, double* __restrict__ q, double* __restrict__ P, const float* __restrict__ gyr,
-                  const float* __restrict__ ang, int ang_xyzw, double Dt, double g_noise, double s_eps) {
+                  const float* __restrict__ ang, int ang_xyzw, double Dt, double g_noise, double s_eps,
+                  float4* __restrict__ q_f32_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     EKF4 s;
@@ -130,6 +131,8 @@ ekf_update_kernel(int64_t n, double* __restrict__ q, double* __restrict__ P, con
     for (int k = 0; k < 4; ++k) q[(int64_t)k * n + i] = s.q[k];
 #pragma unroll
     for (int k = 0; k < 16; ++k) P[(int64_t)k * n + i] = s.P[k / 4][k % 4];
+    // torch.Tensor(self.Q_state): float64 -> float32 wxyz, the PV filter's orientation input (ekf_lee_landed.py:402)
+    if (q_f32_out) q_f32_out[i] = make_float4((float)s.q[0], (float)s.q[1], (float)s.q[2], (float)s.q[3]);
 }
 
 __global__ void ekf_init_kernel(int64_t n, double* q, double* P) {
@@ -171,6 +174,98 @@ __global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float 
             if (mode >= 2) v = v * (u01(rr[j]) * noise_range + noise_lo);
             out[i * d + j0 + j] = v;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ E3 glue
+// Sensor front-end of EKFLeeLanded.pre_physics_step (tasks/ekf_lee_landed.py:345-346,366-375,397-406): from the true root
+// state builds, per env, sensors[16] = accel(3) | gyr(3) | ang xyzw(4) | pos(3) | vel(3), optionally through the
+// sensor-fault model (after the warm-up).  accel = (linvel - prev_linvel)/dt with +9.8 on z (the reference adds 9.8, not
+// 9.81, in place -- :367 -- so the PV filter receives the gravity-added, un-rotated vector).  prev_linvel is updated (:454).
+struct FrontArgs {
+    int64_t n;
+    const float* root13;
+    float* prev_linvel;      // [n,3] in/out
+    float* sensors;          // [n,16] out
+    float dt;
+    int mode;                // 0: truth (warm-up) ; 1..3: OZL_POMDP_*
+    float flicker_p, noise_lo, noise_range;
+    uint64_t seed, step;
+    uint32_t env_id_base;
+};
+__device__ __forceinline__ void fault3(const FrontArgs& a, uint32_t genv, uint32_t stream, bool per_env_flicker, float* v, int d) {
+    if (a.mode == 0) return;
+    bool black = false;
+    if (a.mode == 1 || a.mode == 3) {
+        // batched calls draw ONE flicker value for all envs; the per-env `ang` call draws one per env (ekf_lee_landed.py:383)
+        const uint4 r = draw(a.seed, per_env_flicker ? genv : GLOBAL_ENV, a.step, P_FLICKER + (stream << 8));
+        black = u01(r.x) <= a.flicker_p;
+    }
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (a.mode >= 2) r = draw(a.seed, genv, a.step, P_OBSNOISE + (stream << 8));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    for (int j = 0; j < d; ++j) {
+        float x = black ? 0.0f : v[j];
+        if (a.mode >= 2) x = x * (u01(rr[j]) * a.noise_range + a.noise_lo);
+        v[j] = x;
+    }
+}
+__global__ void sensor_frontend_kernel(const FrontArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float* r = a.root13 + i * 13;
+    const uint32_t genv = a.env_id_base + (uint32_t)i;
+    float acc[3], gyr[3], ang[4], pos[3], vel[3];
+    for (int j = 0; j < 3; ++j) {
+        acc[j] = (r[7 + j] - a.prev_linvel[i * 3 + j]) / a.dt;           // :345-346
+        gyr[j] = r[10 + j]; pos[j] = r[j]; vel[j] = r[7 + j];
+    }
+    acc[2] = acc[2] + 9.8f;                                              // :367
+    for (int j = 0; j < 4; ++j) ang[j] = r[3 + j];
+    fault3(a, genv, 1, false, gyr, 3);                                   // :374
+    fault3(a, genv, 3, true, ang, 4);                                    // :383
+    fault3(a, genv, 4, false, acc, 3);                                   // :401
+    fault3(a, genv, 5, false, pos, 3);                                   // :403
+    fault3(a, genv, 6, false, vel, 3);                                   // :404
+    float* o = a.sensors + i * 16;
+    for (int j = 0; j < 3; ++j) { o[j] = acc[j]; o[3 + j] = gyr[j]; o[10 + j] = pos[j]; o[13 + j] = vel[j]; }
+    for (int j = 0; j < 4; ++j) o[6 + j] = ang[j];
+    for (int j = 0; j < 3; ++j) a.prev_linvel[i * 3 + j] = r[7 + j];     // :454
+}
+
+// Waypoint ("carrot") logic + controller input assembly (tasks/ekf_lee_landed.py:458-503).
+//   warm-up: waypoint = target, controller runs on the true state
+//   after:   if waypoint_dist < 0.5 or > 1.0: waypoint = pos + 0.75 * unit(target + (0,0,0.7) - pos)
+//            if target_dist < 0.75:           waypoint = target + (0,0,0.09)
+//            controller state = [PV position, true quat, PV velocity, true angvel]
+// The reference guards the carrot update with a GLOBAL `(waypoint_dist == 0).any()` (:474); here the guard is per env.
+__global__ void waypoint_kernel(int64_t n, const float* __restrict__ root13, const float* __restrict__ pv_x,
+                                const float* __restrict__ target3, float* __restrict__ waypoint3, int warm,
+                                float* __restrict__ est13, float4* __restrict__ cmd4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = root13 + i * 13;
+    const float p[3] = {r[0], r[1], r[2]}, t[3] = {target3[i * 3], target3[i * 3 + 1], target3[i * 3 + 2]};
+    float w[3] = {waypoint3[i * 3], waypoint3[i * 3 + 1], waypoint3[i * 3 + 2]};
+    if (warm) { w[0] = t[0]; w[1] = t[1]; w[2] = t[2]; }                                   // :461-463
+    const float tv[3] = {t[0] - p[0], t[1] - p[1], t[2] - p[2]};
+    const float td = sqrtf((tv[0] * tv[0] + tv[1] * tv[1]) + tv[2] * tv[2]);
+    const float wv[3] = {w[0] - p[0], w[1] - p[1], w[2] - p[2]};
+    const float wd = sqrtf((wv[0] * wv[0] + wv[1] * wv[1]) + wv[2] * wv[2]);
+    if (!warm) {
+        if ((wd < 0.5f || wd > 1.0f) && wd != 0.0f) {                                       // :473-482
+            const float rv[3] = {t[0] - p[0], t[1] - p[1], (t[2] + 0.7f) - p[2]};
+            const float rd = sqrtf((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+            for (int j = 0; j < 3; ++j) w[j] = (rv[j] / rd) * 0.75f + p[j];
+        }
+        if (td < 0.75f) { w[0] = t[0]; w[1] = t[1]; w[2] = t[2] + 0.09f; }                  // :483-486
+    }
+    for (int j = 0; j < 3; ++j) waypoint3[i * 3 + j] = w[j];
+    cmd4[i] = make_float4(w[0], w[1], w[2], 0.0f);                                         // :488
+    float* e = est13 + i * 13;
+    for (int j = 0; j < 13; ++j) e[j] = r[j];
+    if (!warm) {                                                                            // :493-497
+        for (int j = 0; j < 3; ++j) { e[j] = pv_x[(int64_t)j * n + i]; e[7 + j] = pv_x[(int64_t)(3 + j) * n + i]; }
     }
 }
 
@@ -277,12 +372,39 @@ extern "C" int ozl_ekf_set_q(int64_t n, double* q4xN, const float* quat_xyzw, co
 }
 
 extern "C" int ozl_ekf_update(int64_t n, double* q4xN, double* P16xN, const float* gyr3, const float* ang4, int32_t ang_xyzw,
-                              double Dt, double g_noise, void* stream) {
+                              double Dt, double g_noise, float* q_wxyz_f32_out, void* stream) {
     OZL_N_CHECK("ozl_ekf_update");
     if (!q4xN || !P16xN || !gyr3 || !ang4) return set_error("ozl_ekf_update: NULL buffer");
     if ((uintptr_t)ang4 & 15) return set_error("ozl_ekf_update: ang4 must be 16-byte aligned");
-    ekf_update_kernel<<<nblk(n, 128), 128, 0, st>>>(n, q4xN, P16xN, gyr3, ang4, ang_xyzw, Dt, g_noise, 0.0000001);
+    if ((uintptr_t)q_wxyz_f32_out & 15) return set_error("ozl_ekf_update: q_wxyz_f32_out must be 16-byte aligned");
+    ekf_update_kernel<<<nblk(n, 128), 128, 0, st>>>(n, q4xN, P16xN, gyr3, ang4, ang_xyzw, Dt, g_noise, 0.0000001,
+                                                    (float4*)q_wxyz_f32_out);
     return check_cuda(cudaGetLastError(), "ekf_update_kernel");
+}
+
+extern "C" int ozl_sensor_frontend(int64_t n, const float* root13, float* prev_linvel3, float* sensors16, float dt,
+                                   int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step, int64_t env_id_base,
+                                   void* stream) {
+    OZL_N_CHECK("ozl_sensor_frontend");
+    if (!root13 || !prev_linvel3 || !sensors16) return set_error("ozl_sensor_frontend: NULL buffer");
+    if (mode < 0 || mode > 3) return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");
+    FrontArgs a;
+    a.n = n; a.root13 = root13; a.prev_linvel = prev_linvel3; a.sensors = sensors16; a.dt = dt; a.mode = mode;
+    a.flicker_p = (mode == 3) ? 0.1f : pomdp_prob;
+    const float lo = (float)(1.0 - (double)pomdp_prob), hi = (float)(1.0 + (double)pomdp_prob);
+    a.noise_lo = lo; a.noise_range = hi - lo;
+    a.seed = seed; a.step = step; a.env_id_base = (uint32_t)env_id_base;
+    sensor_frontend_kernel<<<nblk(n, 256), 256, 0, st>>>(a);
+    return check_cuda(cudaGetLastError(), "sensor_frontend_kernel");
+}
+
+extern "C" int ozl_waypoint_command(int64_t n, const float* root13, const float* pv_x9xN, const float* target3,
+                                    float* waypoint3, int32_t warmup, float* est13, float* cmd4, void* stream) {
+    OZL_N_CHECK("ozl_waypoint_command");
+    if (!root13 || !target3 || !waypoint3 || !est13 || !cmd4 || (!warmup && !pv_x9xN)) return set_error("ozl_waypoint_command: NULL buffer");
+    if ((uintptr_t)cmd4 & 15) return set_error("ozl_waypoint_command: cmd4 must be 16-byte aligned");
+    waypoint_kernel<<<nblk(n, 256), 256, 0, st>>>(n, root13, pv_x9xN, target3, waypoint3, warmup, est13, (float4*)cmd4);
+    return check_cuda(cudaGetLastError(), "waypoint_kernel");
 }
 
 extern "C" int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step,

@@ -360,6 +360,48 @@ __global__ void set_params_kernel(const Planes pl, int64_t n, const float* param
     store_static(pl, i, e);
 }
 
+// reset phase only (see ozl_apply_resets): same draws as env_step, no physics, no bookkeeping
+__global__ void apply_resets_kernel(const DevCfg c, const Planes pl, const int64_t* __restrict__ reset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.num_envs || reset[i] == 0) return;
+    const uint64_t step = ld_relaxed(pl.ctrl);
+    Loaded L;
+    load_env(pl, i, L);
+    Env e;
+    unpack(L, e);
+    const uint32_t genv = c.env_id_base + (uint32_t)i;
+    const uint32_t landed = e.fault & LANDED_BIT;
+    if (!c.target_fixed) {
+        const uint4 r = draw(c.seed, genv, step, P_TARGET);
+        e.tgt[0] = u01(r.x) * c.target_scale[0] + c.target_off[0];
+        e.tgt[1] = u01(r.y) * c.target_scale[1] + c.target_off[1];
+        e.tgt[2] = u01(r.z) * c.target_scale[2] + c.target_off[2];
+    }
+    const uint4 r = draw(c.seed, genv, step, P_SPAWN);
+    e.p[0] = c.spawn_base[0] + (c.spawn_range[0] * u01(r.x) + c.spawn_lo[0]);
+    e.p[1] = c.spawn_base[1] + (c.spawn_range[1] * u01(r.y) + c.spawn_lo[1]);
+    e.p[2] = c.spawn_base[2] + (c.spawn_range[2] * u01(r.z) + c.spawn_lo[2]);
+    e.q[0] = e.q[1] = e.q[2] = 0.0f; e.q[3] = 1.0f;
+    for (int j = 0; j < 3; ++j) { e.v[j] = 0.0f; e.w[j] = 0.0f; }
+    if (c.fault_mode) {
+        const uint4 f = draw(c.seed, genv, step, P_FAULT);
+        e.fault = (f.x & 3u) | (__umulhi(f.y, (uint32_t)c.max_episode_length) << 2) | landed;
+        e.eff = c.fault_eff_lo + c.fault_eff_range * u01(f.z);
+    }
+    if (c.dr_enable) {
+        const uint4 a = draw(c.seed, genv, step, P_DR0), b = draw(c.seed, genv, step, P_DR1);
+        e.mass = c.mass * (c.dr_lo + c.dr_range * u01(a.x));
+        e.inv_m = 1.0f / e.mass;
+        e.ixx = c.ixx * (c.dr_lo + c.dr_range * u01(a.y));
+        e.iyy = c.iyy * (c.dr_lo + c.dr_range * u01(a.z));
+        e.izz = c.izz * (c.dr_lo + c.dr_range * u01(a.w));
+        e.arm = c.arm * (c.dr_lo + c.dr_range * u01(b.x));
+        e.ks = 1.0f * (c.dr_lo + c.dr_range * u01(b.y));
+    }
+    store_dynamic(pl, i, e);
+    store_static(pl, i, e);
+}
+
 __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { pl.ctrl[0] = 0ull; pl.ctrl[1] = 0ull; }
@@ -591,6 +633,13 @@ extern "C" int ozl_step_tracking(ozl_env* env, const float* actions, const float
 extern "C" int ozl_step_wrench(ozl_env* env, const float* wrench4, const float* target3, float* obs, float* rew,
                                int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
     return launch_step(env, wrench4, target3, ACT_WRENCH, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step_wrench");
+}
+
+extern "C" int ozl_apply_resets(ozl_env* env, const int64_t* reset, void* stream) {
+    OZL_ENV_CHECK("ozl_apply_resets");
+    if (!reset) return set_error("ozl_apply_resets: reset is NULL");
+    apply_resets_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->dev, env->pl, reset);
+    return check_cuda(cudaGetLastError(), "apply_resets_kernel");
 }
 
 extern "C" int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int64_t* reset, int64_t* progress, void* stream) {

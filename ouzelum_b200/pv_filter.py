@@ -96,8 +96,8 @@ class PVFilterBank:
             a.pos_period = a.vel_period = 1            # no rule given: every env takes a supplied measurement
         a.iter_base = int(iter_base)
         check(lib.ozl_pv_step(C.byref(a), _s()))
-        if keep:
-            torch.cuda.current_stream().synchronize()      # temporaries above must outlive the launch
+        self._keep = keep                                  # inputs may be temporaries: keep them alive past the launch
+        # (same-stream allocator reuse is stream-ordered, so no host synchronisation is needed)
 
     def prediction_step(self, accels, orientation, dt=0.02, sim_time=0, flip_Qw=True):
         """PVFilter.py:25-64, batched."""

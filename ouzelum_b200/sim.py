@@ -64,6 +64,14 @@ class QuadSim:
         check(lib.ozl_rollout(self._h, int(k), obs.data_ptr(), rew.data_ptr(), reset.data_ptr(), progress.data_ptr(),
                               _stream()))
 
+    def apply_resets(self, reset):
+        """ozl_apply_resets: make the pending resets visible in the private state without stepping (idempotent)."""
+        check(lib.ozl_apply_resets(self._h, reset.data_ptr(), _stream()))
+
+    def get_root(self, out):
+        check(lib.ozl_get_state(self._h, out.data_ptr(), None, None, None, _stream()))
+        return out
+
     def reset_all(self, seed=0):
         check(lib.ozl_reset_all(self._h, int(seed), _stream()))
 

@@ -1,4 +1,5 @@
 """Task registry (mirror of `isaacgym_task_map`, isaacgymenvs/tasks/__init__.py:58-85, quadcopter family only)."""
+from .ekf_lee_landed import EKFLeeLanded
 from .landing import Landed, Landing, Lando
 from .lee_landed import LeeLanded
 from .ouzelum import Ouzelum
@@ -10,5 +11,6 @@ task_map = {
     "Landing": Landing,
     "Landed": Landed,
     "LeeLanded": LeeLanded,
+    "EKFLeeLanded": EKFLeeLanded,
     "Quadcopter": Quadcopter,
 }

@@ -189,3 +189,62 @@ def test_quadcopter_task_bit_exact_vs_oracle_config1():
     alive = env.progress_buf == 21                      # envs that were not re-spawned meanwhile (dist > 3 or z < 0.3)
     assert int(alive.sum()) > n // 4
     assert float((env.root_states[:, 2] - z0)[alive].abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("pomdp", ["none", "random_noise"])
+def test_ekf_lee_landed_glue_vs_oracle(pomdp):
+    """Whole estimator / controller chain of EKFLeeLanded against the composite oracle, step by step from identical
+    state (the GPU's own root state and filter states are copied into the oracle before each step)."""
+    import ouzelum_b200
+    from oracle.ekf_lee_landed import EKFLeeGlue
+    n, conv = 96, 6
+    cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=4, ConvergenceTime=conv, POMDP=pomdp, pomdp_prob=0.05,
+                                   maxEpisodeLength=25)
+    env = ouzelum_b200.make(seed=4, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
+    mode = {"none": 0, "random_noise": 2}[pomdp]
+    ora = EKFLeeGlue(n, convergence=conv, pomdp_mode=mode, pomdp_prob=0.05, seed=4)
+    a = torch.zeros(n, 4, device=DEV)
+    for t in range(40):
+        reset_before = env.reset_buf.bool().cpu().numpy().copy()
+        # identical inputs for the oracle: filter states as they stand on the GPU before the step
+        ora.Q = env.ekf.Q_state.cpu().numpy().copy()
+        ora.ekf.P = env.ekf.P.cpu().numpy().copy()
+        ora.pv.state = env.pvfilters.get_states().cpu().numpy().copy()
+        ora.pv.cov = env.pvfilters.get_covariances().cpu().numpy().copy()
+        ora.prev_v = env.prev_root_linvels.cpu().numpy().copy()
+        ora.waypoints = env.target_waypoints.cpu().numpy().copy()
+        env.step(a)
+        root = env._root.cpu().numpy()                       # post-reset, pre-physics truth the chain ran on
+        tgt = env._target.cpu().numpy()
+        wrench, est, cmd = ora.pre_physics(root, tgt, reset_before)
+        warm = t < conv
+        np.testing.assert_allclose(env._cmd.cpu().numpy(), cmd, rtol=1e-5, atol=1e-5, err_msg=f"cmd t={t}")
+        np.testing.assert_allclose(env.ekf.Q_state.cpu().numpy(), ora.Q, rtol=1e-9, atol=1e-12, err_msg=f"Q t={t}")
+        sx = np.abs(ora.pv.state).max() + 1.0
+        np.testing.assert_allclose(env.pvfilters.get_states().cpu().numpy(), ora.pv.state, rtol=2e-3, atol=2e-4 * sx, err_msg=f"pv t={t}")
+        if warm:
+            assert np.array_equal(env._hover.cpu().numpy(), wrench)
+        else:
+            np.testing.assert_allclose(env._est.cpu().numpy(), est, rtol=2e-3, atol=2e-4 * sx, err_msg=f"est t={t}")
+            # the controller amplifies estimate differences by its gains: compare it on the GPU's own estimate
+            from oracle.lee_control import lee_control
+            th, tq = lee_control(env._est.cpu().numpy(), env._cmd.cpu().numpy(), mode=0)
+            w = env._wrench.cpu().numpy()
+            np.testing.assert_allclose(w[:, 0], ora.mg * th, rtol=2e-5, atol=2e-4)
+            np.testing.assert_allclose(w[:, 1:], tq, rtol=2e-5, atol=1e-4)
+    assert env.sim_step_count == 40 and env.episodes > 0
+
+
+def test_ekf_lee_landed_closed_loop_lands():
+    """End-to-end results check in the spirit of the reference's only recorded figure (23 landings / 26 episodes for the
+    RL `Landed` task): the classical EKF+Lee pipeline must bring most vehicles onto the moving target."""
+    import ouzelum_b200
+    n = 256
+    cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=1, POMDP="random_noise", pomdp_prob=0.02, ConvergenceTime=50)
+    env = ouzelum_b200.make(seed=1, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
+    a = torch.zeros(n, 4, device=DEV)
+    for t in range(2200):
+        env.step(a)
+    assert env.episodes >= n
+    frac = env.landings / env.episodes
+    assert frac > 0.5, (env.landings, env.episodes)
