@@ -189,10 +189,9 @@ def run_ours(args):
     import ouzelum_b200
     from ouzelum_b200 import _lib
     from ouzelum_b200.sim import QuadSim
+    from ouzelum_b200.dist import allreduce_metrics, rank_info
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = rank_info()
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
@@ -228,7 +227,7 @@ def run_ours(args):
         if world > 1:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                dist.all_reduce(metrics_dev, op=dist.ReduceOp.SUM)
+                allreduce_metrics(metrics_dev)
 
     clocks = ClockSampler(local)
     clocks.start()

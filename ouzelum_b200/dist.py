@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: env sharding and the metrics all-reduce (the only collective on the path).
+
+Envs are independent, so N_total envs are split into contiguous blocks of global env ids, one process per
+GPU; the counter RNG is keyed by GLOBAL env id, so results do not depend on the number of ranks.  No per-step
+communication.  `torch.distributed` (NCCL over NVLink on the GPUs, gloo in the CPU tests) is plumbing only.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def rank_info():
+    """(rank, world_size, local_rank) from the torchrun environment (defaults: single process)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard(total_envs: int, rank: int, world: int):
+    """Contiguous block owned by `rank`: returns (num_local_envs, env_id_base).  The first `total % world` ranks get one
+    extra env, so any total is covered exactly once."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    q, r = divmod(int(total_envs), int(world))
+    n = q + (1 if rank < r else 0)
+    base = rank * q + min(rank, r)
+    return n, base
+
+
+def allreduce_metrics(metrics: torch.Tensor, async_op: bool = False):
+    """Sum the 16-double metrics vector over all ranks (in place).  No-op without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.all_reduce(metrics, op=dist.ReduceOp.SUM, async_op=async_op)
+    return None
+
+
+def summarize(metrics: torch.Tensor):
+    """Human-readable episode / reward statistics from a (reduced) metrics vector."""
+    m = metrics.detach().cpu().tolist()
+    steps, eps = max(m[8], 1.0), max(m[9], 1.0)
+    return {"env_steps": m[8], "episodes": m[9], "mean_reward": m[0] / steps, "mean_episode_return": m[1] / eps,
+            "mean_episode_length": m[10] / eps, "timeouts": m[11], "crash_dist": m[12], "crash_z": m[13],
+            "fault_active_frac": m[14] / steps, "landed_episodes": m[2], "resets": m[15]}
