@@ -107,6 +107,14 @@ int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream);
 int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
              uint8_t* timeout, float* ep_ret, void* stream);
 
+/* Zero-copy variant for a HOST consumer: `actions_host`, `obs_host`, `rew_host`, `done_host` are page-locked host buffers
+ * mapped into the device address space (cudaHostAlloc / torch pinned memory: under UVA the host pointer IS the device
+ * pointer).  The kernel reads the actions and writes observation, reward and a compact done flag (u8) straight across
+ * PCIe, so one control step is one launch + one stream synchronise -- no separate H2D/D2H copies.  reset / progress stay
+ * in device memory.  Replaces the `.to(rl_device)` copies of VecTask.step (vec_task.py:353-359) when rl_device is the CPU. */
+int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                  int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
+
 /* Same step with the target supplied by the caller every step instead of being re-sampled in-kernel: the landing
  * family, whose target rides on a ground vehicle (tasks/landing.py:373-374, lando.py, landed.py).  target3 [N,3] f32. */
 int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,

@@ -98,6 +98,7 @@ _SIGS = {
     "ozl_destroy": (C.c_int, [_P]),
     "ozl_reset_all": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_step": (C.c_int, [_P] * 9),
+    "ozl_step_host": (C.c_int, [_P] * 10),
     "ozl_step_tracking": (C.c_int, [_P] * 10),
     "ozl_step_wrench": (C.c_int, [_P] * 10),
     "ozl_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

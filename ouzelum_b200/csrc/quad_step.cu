@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
 quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
-                 const int act_mode) {
+                 const int act_mode, uint8_t* __restrict__ done_u8, const int obs_bulk) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
     __shared__ double s_m[BLOCK / 32][11];
 
@@ -181,6 +181,7 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         progress[i] = o.prog;
         if (timeout) timeout[i] = o.timeout ? 1 : 0;
         if (ep_ret_out) ep_ret_out[i] = o.ep_ret_done;
+        if (done_u8) done_u8[i] = o.reset ? 1 : 0;
 #pragma unroll
         for (int j = 0; j < 13; ++j) s_obs[threadIdx.x * 13 + j] = o.obs[j];   // stride 13: conflict-free
     }
@@ -196,7 +197,13 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         const int nflt = n_here * 13;
         if ((nflt & 3) == 0) {   // base*13*4 bytes is 16-byte aligned whenever BLOCK % 4 == 0
 #if OZL_OBS_BULK
-            if (threadIdx.x == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
+            if (obs_bulk) {
+                if (threadIdx.x == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
+            } else {
+                float4* d4p = reinterpret_cast<float4*>(dst);
+                const float4* s4 = reinterpret_cast<const float4*>(s_obs);
+                for (int k = threadIdx.x; k < nflt / 4; k += BLOCK) d4p[k] = s4[k];
+            }
 #else
             float4* d4p = reinterpret_cast<float4*>(dst);
             const float4* s4 = reinterpret_cast<const float4*>(s_obs);
@@ -609,19 +616,29 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 constexpr int kStepBlock = OZL_STEP_BLOCK;
 
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
-                       int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who) {
+                       int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
+                       uint8_t* done_u8 = nullptr, int obs_bulk = 1) {
     if (!env) return set_error("%s: env is NULL", who);
     cudaStream_t st = (cudaStream_t)stream;
     if (!actions || !obs || !rew || !reset || !progress) return set_error("%s: NULL buffer", who);
     if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("%s: actions/obs must be 16-byte aligned", who);
     quad_step_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
-        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode);
+        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8,
+        obs_bulk);
     return check_cuda(cudaGetLastError(), "quad_step_kernel");
 }
 
 extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
                         uint8_t* timeout, float* ep_ret, void* stream) {
     return launch_step(env, actions, nullptr, ACT_ROTORS, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step");
+}
+
+extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                             int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    if (!done_host) return set_error("ozl_step_host: done_host is NULL");
+    // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store
+    return launch_step(env, actions_host, nullptr, ACT_ROTORS, obs_host, rew_host, reset, progress, timeout, ep_ret, stream,
+                       "ozl_step_host", done_host, 0);
 }
 
 extern "C" int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,

@@ -50,6 +50,14 @@ class QuadSim:
         check(lib.ozl_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(), reset.data_ptr(),
                            progress.data_ptr(), ptr(timeout), ptr(ep_ret), _stream()))
 
+    def step_host(self, actions_host, obs_host, rew_host, done_host, reset, progress, timeout=None, ep_ret=None):
+        """ozl_step_host: actions / obs / rew / done are PINNED host tensors accessed zero-copy by the kernel."""
+        for t in (actions_host, obs_host, rew_host, done_host):
+            if not t.is_pinned():
+                raise ValueError("step_host needs page-locked (pinned) host tensors")
+        check(lib.ozl_step_host(self._h, actions_host.data_ptr(), obs_host.data_ptr(), rew_host.data_ptr(),
+                                done_host.data_ptr(), reset.data_ptr(), progress.data_ptr(), ptr(timeout), ptr(ep_ret), _stream()))
+
     def step_tracking(self, actions, target, obs, rew, reset, progress, timeout=None, ep_ret=None):
         """ozl_step_tracking: the target [N,3] is supplied by the caller (landing family)."""
         check(lib.ozl_step_tracking(self._h, actions.data_ptr(), target.data_ptr(), obs.data_ptr(), rew.data_ptr(),

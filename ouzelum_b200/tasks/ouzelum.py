@@ -101,6 +101,20 @@ class X500Task(VecTask):
         self._static_actions.copy_(actions)
         self._graph.replay()
 
+    # ---- host-consumer step ----------------------------------------------------------------------------------
+    def step_host(self, actions_host):
+        """`step` for a consumer that lives on the CPU (rl_device == "cpu" in the reference's terms, vec_task.py:353-359):
+        `actions_host` is a pinned [N,4] float32 CPU tensor; returns pinned CPU tensors (obs [N,13], reward [N], done [N] u8)
+        that are valid when the call returns.  The kernel reads / writes them in place across PCIe (zero-copy)."""
+        if not hasattr(self, "_h_obs"):
+            pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()
+            self._h_obs, self._h_rew = pin(self.num_envs, self.num_obs), pin(self.num_envs)
+            self._h_done = pin(self.num_envs, dt=torch.uint8)
+        self.sim.step_host(actions_host, self._h_obs, self._h_rew, self._h_done, self.reset_buf, self.progress_buf,
+                           self._timeout_u8, self.episode_return_buf)
+        torch.cuda.current_stream().synchronize()
+        return self._h_obs, self._h_rew, self._h_done
+
     # ---- reference-style state views (copies out of the private SoA state) ------------------------------
     @property
     def root_states(self):

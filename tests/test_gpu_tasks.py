@@ -248,3 +248,22 @@ def test_ekf_lee_landed_closed_loop_lands():
     assert env.episodes >= n
     frac = env.landings / env.episodes
     assert frac > 0.5, (env.landings, env.episodes)
+
+
+def test_step_host_zero_copy_matches_device_step():
+    """Host-consumer API: pinned actions in, pinned obs / reward / done out, identical to the device-buffer step."""
+    import ouzelum_b200
+    n = 1500
+    mk = lambda: ouzelum_b200.make(seed=9, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                   cfg=ouzelum_b200.task_config("Ouzelum", n, seed=9, rotorFault={"enable": True}))
+    e1, e2 = mk(), mk()
+    g = torch.Generator().manual_seed(3)
+    for t in range(60):
+        a = (torch.rand(n, 4, generator=g) * 2 - 1).pin_memory()
+        o1, r1, d1, _ = e1.step(a.to(DEV))
+        ho, hr, hd = e2.step_host(a)
+        assert not ho.is_cuda and ho.is_pinned()
+        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu().to(torch.uint8), hd), t
+    assert torch.equal(e1.reset_buf, e2.reset_buf) and torch.equal(e1.progress_buf, e2.progress_buf)
+    with pytest.raises(ValueError):
+        e2.step_host(torch.zeros(n, 4))          # not pinned
