@@ -106,17 +106,34 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rate(n_envs, budget_s, seed, max_steps=None):
-    """Times the oracle port of the reference step (torch-CPU eager, all host threads) on a bounded sample.
-    Returns (env-steps/s, steps run, envs per step, threads)."""
+def _cpu_oracle(n_envs, seed, flavour):
+    """flavour "c": the multi-threaded C restatement (oracle/quad_step_c.c, OpenMP over envs) -- the strongest CPU arm;
+    flavour "torch": the torch-CPU eager restatement (same op sequence as the reference's Python, oracle/quad_step.py)."""
     import torch
     from oracle.quad_step import QuadStepOracle, default_cfg
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     cfg = default_cfg(n_envs, seed=seed, **{k: v for k, v in task_cfg_kwargs().items() if k != "collect_metrics"})
+    if flavour == "c":
+        from oracle.c_oracle import COracle, make_cfg
+        ora = COracle(make_cfg(QuadStepOracle(cfg).cfg))          # QuadStepOracle rounds the float fields exactly like the struct
+        return ora, (lambda a: ora.step(a.numpy()))
+    torch.set_num_threads(os.cpu_count() or 1)
     ora = QuadStepOracle(cfg)
+    return ora, ora.step
+
+
+def cpu_port_rate(n_envs, budget_s, seed, max_steps=None, flavour="c"):
+    """Times an oracle port of the reference step on all host threads, on a bounded sample.
+    Returns (env-steps/s, steps run, envs per step, threads)."""
+    import torch
+    threads = os.cpu_count() or 1
+    _, step = _cpu_oracle(n_envs, seed, flavour)
     g = torch.Generator().manual_seed(seed)
     acts = [torch.rand(n_envs, 4, generator=g) * 2 - 1 for _ in range(4)]
+
+    class _O:
+        pass
+    ora = _O()
+    ora.step = step
     for k in range(2):
         ora.step(acts[k])                       # warm-up (allocator, thread pool)
     t0 = time.perf_counter()
@@ -142,30 +159,28 @@ def run_reference(args):
     n = args.envs
     # bound the run: K+W steps of the full workload if that fits ~2 minutes, else a smaller env sample per step
     import torch
-    from oracle.quad_step import QuadStepOracle, default_cfg
     threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
 
     def mk(m):
-        return QuadStepOracle(default_cfg(m, seed=args.seed, **{k: v for k, v in task_cfg_kwargs().items() if k != "collect_metrics"}))
+        return _cpu_oracle(m, args.seed, "c")[1]
     probe = mk(n)
     a = torch.rand(n, 4) * 2 - 1
-    probe.step(a)
+    probe(a)
     t0 = time.perf_counter()
-    probe.step(a)
+    probe(a)
     per = time.perf_counter() - t0
     total = per * (args.steps + args.warmup)
     sample = n
     if total > 120.0:
         sample = max(256, int(n * 120.0 / total) // 256 * 256)
-    ora = mk(sample)
+    step = mk(sample)
     g = torch.Generator().manual_seed(args.seed)
     acts = [torch.rand(sample, 4, generator=g) * 2 - 1 for _ in range(4)]
     for k in range(args.warmup):
-        ora.step(acts[k & 3])
+        step(acts[k & 3])
     t0 = time.perf_counter()
     for k in range(args.steps):
-        ora.step(acts[k & 3])
+        step(acts[k & 3])
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {
@@ -173,7 +188,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_step": sample,
-                   "note": "CPU restatement of the reference step (PhysX unavailable): oracle port, torch-CPU eager"},
+                   "note": "CPU restatement of the reference step (PhysX unavailable): C port of the oracle, OpenMP over envs, all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {sample} envs of the workload (host cores only)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -389,9 +404,11 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, steps_c, envs_c, threads = cpu_port_rate(n, budget_s=12.0, seed=args.seed)
+        v, steps_c, envs_c, threads = cpu_port_rate(n, budget_s=8.0, seed=args.seed, flavour="c")
+        vt, steps_t, envs_t, _ = cpu_port_rate(n, budget_s=6.0, seed=args.seed, flavour="torch")
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{steps_c} steps x {envs_c} envs (oracle port of the reference step, torch-CPU eager; PhysX unavailable)"}
+               "sample": f"{steps_c} steps x {envs_c} envs (C restatement of the reference step, OpenMP over envs; PhysX unavailable)",
+               "torch_eager_port": {"value": vt, "sample": f"{steps_t} steps x {envs_t} envs (torch-CPU eager restatement, the reference's own op-by-op style)"}}
 
     if rank == 0:
         line = {

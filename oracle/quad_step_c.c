@@ -1,0 +1,205 @@
+/* C restatement of the fused x500 env step -- TEST INFRASTRUCTURE (second, independent CPU oracle + the multi-threaded
+ * CPU baseline of bench.py).  Same float32 operation order as oracle/quad_step.py (QuadStepOracle, rotor-action mode) and
+ * as the CUDA kernel; compile with -ffp-contract=off so that nothing is fused.  Reference lines restated:
+ *   isaacgymenvs/tasks/base/vec_task.py:313-359, isaacgymenvs/tasks/ouzelum.py:180-332,
+ *   isaacgymenvs/utils/torch_jit_utils.py:66-71,198-208, isaacgymenvs/utils/POMDP.py:23-42;
+ *   gym.simulate -> the integrator of SURVEY.md 8a row P.
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC -Iinclude oracle/quad_step_c.c -lm   (oracle/c_oracle.py)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "ouzelum_b200.h"
+
+enum { P_TARGET = 0, P_SPAWN = 1, P_FAULT = 2, P_DR0 = 3, P_DR1 = 4, P_OBSNOISE = 8, P_FLICKER = 12 };
+#define GLOBAL_ENV 0xFFFFFFFFu
+#define FAULT_NEVER 0x1FFFFFFF
+
+static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static void draw(uint64_t seed, uint32_t env, uint64_t step, uint32_t purpose, uint32_t out[4]) {
+    philox(env, (uint32_t)step, (uint32_t)(step >> 32), purpose, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+static float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
+
+typedef struct {
+    float h, hh, max_angvel2, inv3, half, inv_pi, flicker_p, noise_lo, noise_range;
+    float sinc_c1, sinc_c2, cos_c1, cos_c2, cos_c3;
+    int nsub;
+} derived_t;
+
+static void quat_to_R(const float q[4], float R[3][3]) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+    R[0][0] = 1.0f - 2.0f * (yy + zz); R[0][1] = 2.0f * (xy - wz); R[0][2] = 2.0f * (xz + wy);
+    R[1][0] = 2.0f * (xy + wz); R[1][1] = 1.0f - 2.0f * (xx + zz); R[1][2] = 2.0f * (yz - wx);
+    R[2][0] = 2.0f * (xz - wy); R[2][1] = 2.0f * (yz + wx); R[2][2] = 1.0f - 2.0f * (xx + yy);
+}
+static void mv(float R[3][3], const float v[3], float o[3]) {
+    for (int i = 0; i < 3; ++i) o[i] = (R[i][0] * v[0] + R[i][1] * v[1]) + R[i][2] * v[2];
+}
+static void mtv(float R[3][3], const float v[3], float o[3]) {
+    for (int i = 0; i < 3; ++i) o[i] = (R[0][i] * v[0] + R[1][i] * v[1]) + R[2][i] * v[2];
+}
+static void cross3(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* state arrays (AoS, caller-owned): root [n,13], thrust [n,4], target [n,3], ep_ret [n], params [n,7] =
+ * mass,ixx,iyy,izz,arm,thrust_scale,fault_eff, fault [n,2] = rotor, onset */
+void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, float* thrust, float* target, float* ep_ret,
+                     float* params, int32_t* fault, const float* actions, float* obs, float* rew, int64_t* reset,
+                     int64_t* progress, uint8_t* timeout) {
+    derived_t d;
+    const double h = (double)c->dt / (double)c->substeps;
+    d.h = (float)h; d.hh = (float)(0.5 * h);
+    d.max_angvel2 = (float)((double)c->max_angvel * (double)c->max_angvel);
+    d.inv3 = 1.0f / 3.0f; d.half = 0.5f; d.inv_pi = 1.0f / (float)M_PI;
+    d.flicker_p = (c->pomdp_mode == 3) ? 0.1f : c->pomdp_prob;
+    { const float lo = (float)(1.0 - (double)c->noise_sigma), hi = (float)(1.0 + (double)c->noise_sigma); d.noise_lo = lo; d.noise_range = hi - lo; }
+    d.sinc_c1 = (float)(-1.0 / 6.0); d.sinc_c2 = (float)(1.0 / 120.0);
+    d.cos_c1 = -0.5f; d.cos_c2 = (float)(1.0 / 24.0); d.cos_c3 = (float)(-1.0 / 720.0);
+    d.nsub = c->substeps * c->control_freq_inv;
+    int blackout = 0;
+    if (c->pomdp_mode == 1 || c->pomdp_mode == 3) {
+        uint32_t r[4];
+        draw(c->seed, GLOBAL_ENV, step, P_FLICKER, r);
+        blackout = u01(r[0]) <= d.flicker_p;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t genv = (uint32_t)c->env_id_base + (uint32_t)i;
+        float* rs = root + i * 13; float* T = thrust + i * 4; float* tg = target + i * 3; float* pr = params + i * 7;
+        float p[3] = {rs[0], rs[1], rs[2]}, q[4] = {rs[3], rs[4], rs[5], rs[6]}, v[3] = {rs[7], rs[8], rs[9]}, w[3] = {rs[10], rs[11], rs[12]};
+        int64_t prog = progress[i];
+        const int rst = reset[i] != 0;
+        uint32_t r4[4];
+        int resample = rst || (!c->target_fixed && (prog % c->target_period) == 0);
+        if (c->target_fixed) resample = 0;
+        if (resample) {
+            draw(c->seed, genv, step, P_TARGET, r4);
+            for (int j = 0; j < 3; ++j) tg[j] = u01(r4[j]) * c->target_scale[j] + c->target_off[j];
+        }
+        if (rst) {
+            draw(c->seed, genv, step, P_SPAWN, r4);
+            for (int j = 0; j < 3; ++j) p[j] = c->spawn_base[j] + (c->spawn_range[j] * u01(r4[j]) + c->spawn_lo[j]);
+            q[0] = q[1] = q[2] = 0.0f; q[3] = 1.0f;
+            for (int j = 0; j < 3; ++j) { v[j] = 0.0f; w[j] = 0.0f; }
+            prog = 0;
+            if (c->fault_mode) {
+                draw(c->seed, genv, step, P_FAULT, r4);
+                fault[i * 2] = (int32_t)(r4[0] & 3u);
+                fault[i * 2 + 1] = (int32_t)(((uint64_t)r4[1] * (uint32_t)c->max_episode_length) >> 32);
+                pr[6] = c->fault_eff_lo + c->fault_eff_range * u01(r4[2]);
+            }
+            if (c->dr_enable) {
+                uint32_t a[4], b[4];
+                draw(c->seed, genv, step, P_DR0, a); draw(c->seed, genv, step, P_DR1, b);
+                pr[0] = c->mass * (c->dr_lo + c->dr_range * u01(a[0]));
+                pr[1] = c->ixx * (c->dr_lo + c->dr_range * u01(a[1]));
+                pr[2] = c->iyy * (c->dr_lo + c->dr_range * u01(a[2]));
+                pr[3] = c->izz * (c->dr_lo + c->dr_range * u01(a[3]));
+                pr[4] = c->arm * (c->dr_lo + c->dr_range * u01(b[0]));
+                pr[5] = 1.0f * (c->dr_lo + c->dr_range * u01(b[1]));
+            }
+        }
+        /* thrust command (ouzelum.py:237-248) */
+        float F[4];
+        for (int k = 0; k < 4; ++k) {
+            const float a = fminf(fmaxf(actions[i * 4 + k], -c->clip_actions), c->clip_actions);
+            float t = T[k] + c->thrust_rate * a;
+            t = fmaxf(fminf(t, c->thrust_max), 0.0f);
+            F[k] = rst ? 0.0f : t;
+            T[k] = F[k];
+            F[k] = F[k] * pr[5];
+        }
+        const int fault_active = c->fault_mode && prog >= (int64_t)fault[i * 2 + 1];
+        if (fault_active) F[fault[i * 2]] = F[fault[i * 2]] * pr[6];
+        /* rigid body */
+        const float inv_m = 1.0f / pr[0];
+        const float inertia[3] = {pr[1], pr[2], pr[3]}, inv_i[3] = {1.0f / pr[1], 1.0f / pr[2], 1.0f / pr[3]};
+        const float fz = ((F[0] + F[1]) + F[2]) + F[3];
+        const float tau_b[3] = {pr[4] * (((F[1] - F[0]) + F[2]) - F[3]), pr[4] * (((F[1] - F[0]) - F[2]) + F[3]),
+                                c->yaw_km * (((F[2] - F[0]) - F[1]) + F[3])};
+        float R[3][3], fw[3], tau_w[3], rc[3], x[3], t3[3];
+        quat_to_R(q, R);
+        for (int j = 0; j < 3; ++j) fw[j] = R[j][2] * fz;
+        mv(R, tau_b, tau_w);
+        for (int j = 0; j < 3; ++j) { rc[j] = c->com_z * R[j][2]; x[j] = p[j] + rc[j]; }
+        cross3(w, rc, t3);
+        for (int j = 0; j < 3; ++j) v[j] = v[j] + t3[j];
+        const float g[3] = {0.0f, 0.0f, c->gravity_z};
+        for (int s = 0; s < d.nsub; ++s) {
+            for (int j = 0; j < 3; ++j) { const float acc = ((fw[j] - c->lin_drag * v[j]) * inv_m) + g[j]; v[j] = v[j] + d.h * acc; }
+            float wb[3], tb[3], iw[3], gy[3];
+            mtv(R, w, wb); mtv(R, tau_w, tb);
+            for (int j = 0; j < 3; ++j) iw[j] = inertia[j] * wb[j];
+            cross3(wb, iw, gy);
+            for (int j = 0; j < 3; ++j) wb[j] = wb[j] + d.h * ((tb[j] - gy[j]) * inv_i[j]);
+            mv(R, wb, w);
+            float n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
+            if (n2 > d.max_angvel2) { const float sc = c->max_angvel / sqrtf(n2); for (int j = 0; j < 3; ++j) w[j] = w[j] * sc; }
+            for (int j = 0; j < 3; ++j) x[j] = x[j] + d.h * v[j];
+            n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
+            const float th2 = (d.hh * d.hh) * n2;
+            const float sinc = 1.0f + th2 * (d.sinc_c1 + th2 * d.sinc_c2);
+            const float cs = 1.0f + th2 * (d.cos_c1 + th2 * (d.cos_c2 + th2 * d.cos_c3));
+            const float k = d.hh * sinc;
+            const float px = k * w[0], py = k * w[1], pz = k * w[2];
+            const float nx = (q[3] * px + (py * q[2] - pz * q[1])) + q[0] * cs;
+            const float ny = (q[3] * py + (pz * q[0] - px * q[2])) + q[1] * cs;
+            const float nz = (q[3] * pz + (px * q[1] - py * q[0])) + q[2] * cs;
+            const float nw = q[3] * cs - ((px * q[0] + py * q[1]) + pz * q[2]);
+            const float inv = 1.0f / sqrtf(((nx * nx + ny * ny) + nz * nz) + nw * nw);
+            q[0] = nx * inv; q[1] = ny * inv; q[2] = nz * inv; q[3] = nw * inv;
+            quat_to_R(q, R);
+        }
+        for (int j = 0; j < 3; ++j) rc[j] = c->com_z * R[j][2];
+        cross3(w, rc, t3);
+        for (int j = 0; j < 3; ++j) { p[j] = x[j] - rc[j]; v[j] = v[j] - t3[j]; }
+        /* post_physics_step: obs (ouzelum.py:280-285), reward (:302-332) */
+        prog += 1;
+        float o[13];
+        const float dx = tg[0] - p[0], dy = tg[1] - p[1], dz = tg[2] - p[2];
+        o[0] = dx * d.inv3; o[1] = dy * d.inv3; o[2] = dz * d.inv3;
+        for (int j = 0; j < 4; ++j) o[3 + j] = q[j];
+        for (int j = 0; j < 3; ++j) { o[7 + j] = v[j] * d.half; o[10 + j] = w[j] * d.inv_pi; }
+        const float dist = sqrtf((dx * dx + dy * dy) + dz * dz);
+        const float pos_r = 1.0f / (1.0f + dist * dist);
+        const float ups_z = (2.0f * (q[3] * q[3]) - 1.0f) + (q[2] * q[2]) * 2.0f;
+        const float tilt = fabsf(1.0f - ups_z);
+        const float up_r = (1.0f / (1.0f + tilt * tilt)) * c->up_coef;
+        const float spin = fabsf(w[2]);
+        const float spin_r = 1.0f / (1.0f + spin * spin);
+        const float reward = pos_r + pos_r * (up_r + spin_r);
+        const int die = (dist > c->die_dist) || (p[2] < c->die_z);
+        const int over = prog >= (int64_t)(c->max_episode_length - 1);
+        const int rsout = over ? 1 : die;
+        if (c->pomdp_mode != 0) {
+            if (blackout) for (int j = 0; j < 13; ++j) o[j] = 0.0f;
+            if (c->pomdp_mode >= 2)
+                for (int k = 0; k < 4; ++k) {
+                    draw(c->seed, genv, step, P_OBSNOISE + k, r4);
+                    for (int j = 0; j < 4 && 4 * k + j < 13; ++j) o[4 * k + j] = o[4 * k + j] * (u01(r4[j]) * d.noise_range + d.noise_lo);
+                }
+        }
+        for (int j = 0; j < 13; ++j) obs[i * 13 + j] = fminf(fmaxf(o[j], -c->clip_obs), c->clip_obs);
+        rew[i] = reward;
+        reset[i] = rsout;
+        progress[i] = prog;
+        if (timeout) timeout[i] = (uint8_t)(over && rsout);
+        const float er = ep_ret[i] + reward;
+        ep_ret[i] = rsout ? 0.0f : er;
+        for (int j = 0; j < 3; ++j) { rs[j] = p[j]; rs[7 + j] = v[j]; rs[10 + j] = w[j]; }
+        for (int j = 0; j < 4; ++j) rs[3 + j] = q[j];
+    }
+}
+
+int ozl_oracle_cfg_size(void) { return (int)sizeof(ozl_cfg); }

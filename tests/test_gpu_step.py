@@ -148,3 +148,29 @@ def test_errors_are_loud():
         QuadSim(_lib.default_cfg(8, substeps=0), "cuda:0")
     with pytest.raises(RuntimeError):
         QuadSim(_lib.default_cfg(8, pomdp_mode=9), "cuda:0")
+
+
+def test_kernel_vs_c_oracle_long_rollout():
+    """Second, independent oracle (C restatement): 400 steps x 4096 envs with faults + DR, bit-exact."""
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+    from oracle.c_oracle import COracle
+    n = 4096
+    cfg = _lib.default_cfg(n, seed=31, fault_mode=1, dr_enable=1, max_episode_length=150)
+    sim, co = QuadSim(cfg, "cuda:0"), COracle(cfg)
+    dev = torch.device("cuda:0")
+    b = dict(obs=torch.zeros(n, 13, device=dev), rew=torch.zeros(n, device=dev),
+             reset=torch.ones(n, dtype=torch.int64, device=dev), progress=torch.zeros(n, dtype=torch.int64, device=dev),
+             timeout=torch.zeros(n, dtype=torch.uint8, device=dev), ep_ret=torch.zeros(n, device=dev))
+    g = torch.Generator().manual_seed(12)
+    for t in range(400):
+        a = (torch.rand(n, 4, generator=g) * 2 - 1) * (0.1 if t % 3 else 1.0)
+        sim.step(a.cuda(), b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+        co.step(a.numpy())
+        if t % 20 == 19 or t < 5:
+            assert np.array_equal(b["reset"].cpu().numpy(), co.reset_buf), t
+            assert np.array_equal(b["progress"].cpu().numpy(), co.progress_buf), t
+            assert np.array_equal(b["obs"].cpu().numpy(), co.obs_buf), t
+            assert np.array_equal(b["rew"].cpu().numpy(), co.rew_buf), t
+    assert np.array_equal(sim.get_state()["root"].cpu().numpy(), co.root)
+    assert int(co.timeout_buf.sum()) >= 0 and int(sim.metrics()[11].item()) > 0      # time-outs happened (max_len 150)
