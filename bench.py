@@ -156,7 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.envs
+    n = args.envs * max(1, int(os.environ.get("WORLD_SIZE", "1")))     # whole-job workload of the GPU arm (weak scaling)
     # bound the run: K+W steps of the full workload if that fits ~2 minutes, else a smaller env sample per step
     import torch
     threads = os.cpu_count() or 1

@@ -78,8 +78,8 @@ class COracle:
         self.lib = C.CDLL(build())
         assert self.lib.ozl_oracle_cfg_size() == C.sizeof(cfg_struct), "ozl_cfg layout mismatch"
         self.cfg = cfg_struct
-        if threads:
-            os.environ["OMP_NUM_THREADS"] = str(threads)
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can
+        self.threads = self.lib.ozl_oracle_set_threads(int(threads or os.cpu_count() or 1))
         n = self.n = int(cfg_struct.num_envs)
         f = np.float32
         self.root = np.zeros((n, 13), f)

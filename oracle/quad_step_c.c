@@ -203,3 +203,10 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
 }
 
 int ozl_oracle_cfg_size(void) { return (int)sizeof(ozl_cfg); }
+
+#ifdef _OPENMP
+#include <omp.h>
+int ozl_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int ozl_oracle_set_threads(int n) { (void)n; return 1; }
+#endif
