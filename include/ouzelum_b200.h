@@ -226,6 +226,40 @@ int ozl_sensor_frontend(int64_t n, const float* root13, float* prev_linvel3, flo
 int ozl_waypoint_command(int64_t n, const float* root13, const float* pv_x9xN, const float* target3, float* waypoint3,
                          int32_t warmup, float* est13, float* cmd4, void* stream);
 
+/* The whole estimator + controller chain of EKFLeeLanded.pre_physics_step (isaacgymenvs/tasks/ekf_lee_landed.py:308-530) as
+ * ONE launch on the envs of `env`: reset handling, sensor front-end + sensor faults, attitude EKF, PV filter with the shared
+ * trigger counters, carrot-waypoint logic, Lee position controller on the estimates, warm-up hover force.  The true root
+ * state is read from the handle's private planes; the step index / warm-up flag come from the handle's device step counter
+ * (CUDA-graph capturable).  Output: wrench4 [N,4] for ozl_step_wrench.  est13 / cmd4 are optional debug outputs (NULL ok). */
+typedef struct ozl_ekf_lee_args {
+    double* ekf_q4xN;
+    double* ekf_P16xN;
+    float* pv_x9xN;
+    float* pv_P81xN;
+    float* prev_linvel3;      /* [N,3] in/out   ekf_lee_landed.py:95,454 */
+    float* waypoint3;         /* [N,3] in/out   :160,461-486             */
+    const float* target3;     /* [N,3]          target riding on the vehicle */
+    const int64_t* reset;     /* [N]            reset_buf                */
+    float* wrench4;           /* [N,4] out      (m g thrust, torque) or the warm-up hover force */
+    float* est13;             /* [N,13] out or NULL */
+    float* cmd4;              /* [N,4] out or NULL  */
+    const float* gains16;     /* HOST: kP, kV, kR, kOmega, scale_input   */
+    float dt;
+    float mg;                 /* 2 * 9.81       :459                     */
+    float hover_force;        /* 2.09 * 9.81    :527                     */
+    int64_t convergence_steps;/* ConvergenceTime :339                    */
+    int32_t pomdp_mode;
+    float pomdp_prob;
+    uint32_t pos_period, pos_phase, vel_period, vel_phase;   /* (7,6,3,0) for 20 / 75 Hz at dt 0.01 */
+    int32_t per_env_triggers; /* 0: the reference's counters shared by all envs; 1: every env counts its own steps */
+    float acc_var[3], pos_var[3];
+    double ekf_Dt, ekf_g_noise;
+} ozl_ekf_lee_args;
+int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* args, void* stream);
+
+/* Device address of the handle's step counter (uint64), for kernels that must follow it without a host round trip. */
+int ozl_step_counter_ptr(ozl_env* env, const uint64_t** out);
+
 /* Sensor-fault model on an [n,d] f32 array.  Replaces POMDPWrapper.observation (isaacgymenvs/utils/POMDP.py:23-42).
  * mode: OZL_POMDP_FLICKER / _NOISE / _FLICKER_NOISE (anything else: the reference's ValueError text).
  * Draws are counter-based: (seed, global env id, step, stream_id) -- stream_id separates several uses in one step. */
@@ -253,6 +287,7 @@ typedef struct ozl_husky_args {
     float* wheels4;
     float* target3;
     uint64_t seed, step;
+    const uint64_t* step_ptr; /* if non-NULL the step index is read from this DEVICE address instead of `step` */
     int64_t env_id_base;
     float dt;             /* 0.01                                      */
     float dist_thresh;    /* 0.2        landing.py:319                 */

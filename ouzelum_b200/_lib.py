@@ -70,9 +70,23 @@ class OzlHuskyArgs(C.Structure):
     _fields_ = [
         ("n", C.c_int64), ("pose4", C.c_void_p), ("idx2", C.c_void_p), ("tables204x2", C.c_void_p), ("reset", C.c_void_p),
         ("wheels4", C.c_void_p), ("target3", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
-        ("env_id_base", C.c_int64), ("dt", C.c_float), ("dist_thresh", C.c_float), ("kp_lin", C.c_float),
+        ("step_ptr", C.c_void_p), ("env_id_base", C.c_int64), ("dt", C.c_float), ("dist_thresh", C.c_float), ("kp_lin", C.c_float),
         ("kp_ang", C.c_float), ("ang_thresh", C.c_float), ("x_offset", C.c_float), ("target_z", C.c_float),
         ("respawn_limit", C.c_float),
+    ]
+
+
+class OzlEkfLeeArgs(C.Structure):
+    """Mirror of `struct ozl_ekf_lee_args` (include/ouzelum_b200.h)."""
+    _fields_ = [
+        ("ekf_q4xN", C.c_void_p), ("ekf_P16xN", C.c_void_p), ("pv_x9xN", C.c_void_p), ("pv_P81xN", C.c_void_p),
+        ("prev_linvel3", C.c_void_p), ("waypoint3", C.c_void_p), ("target3", C.c_void_p), ("reset", C.c_void_p),
+        ("wrench4", C.c_void_p), ("est13", C.c_void_p), ("cmd4", C.c_void_p), ("gains16", C.POINTER(C.c_float)),
+        ("dt", C.c_float), ("mg", C.c_float), ("hover_force", C.c_float), ("convergence_steps", C.c_int64),
+        ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float),
+        ("pos_period", C.c_uint32), ("pos_phase", C.c_uint32), ("vel_period", C.c_uint32), ("vel_phase", C.c_uint32),
+        ("per_env_triggers", C.c_int32), ("acc_var", C.c_float * 3), ("pos_var", C.c_float * 3),
+        ("ekf_Dt", C.c_double), ("ekf_g_noise", C.c_double),
     ]
 
 
@@ -121,6 +135,8 @@ _SIGS = {
                                       C.c_int64, _P]),
     "ozl_waypoint_command": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "ozl_apply_resets": (C.c_int, [_P, _P, _P]),
+    "ozl_ekf_lee_step": (C.c_int, [_P, C.POINTER(OzlEkfLeeArgs), _P]),
+    "ozl_step_counter_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int32, _P, _P, _P]),
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),

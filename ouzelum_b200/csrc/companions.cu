@@ -3,6 +3,7 @@
 #include "internal.h"
 #include "lee_control.cuh"
 #include "filters.cuh"
+#include "glue.cuh"
 
 namespace ozl {
 
@@ -188,28 +189,9 @@ struct FrontArgs {
     float* prev_linvel;      // [n,3] in/out
     float* sensors;          // [n,16] out
     float dt;
-    int mode;                // 0: truth (warm-up) ; 1..3: OZL_POMDP_*
-    float flicker_p, noise_lo, noise_range;
-    uint64_t seed, step;
+    FaultCfg f;
     uint32_t env_id_base;
 };
-__device__ __forceinline__ void fault3(const FrontArgs& a, uint32_t genv, uint32_t stream, bool per_env_flicker, float* v, int d) {
-    if (a.mode == 0) return;
-    bool black = false;
-    if (a.mode == 1 || a.mode == 3) {
-        // batched calls draw ONE flicker value for all envs; the per-env `ang` call draws one per env (ekf_lee_landed.py:383)
-        const uint4 r = draw(a.seed, per_env_flicker ? genv : GLOBAL_ENV, a.step, P_FLICKER + (stream << 8));
-        black = u01(r.x) <= a.flicker_p;
-    }
-    uint4 r = make_uint4(0, 0, 0, 0);
-    if (a.mode >= 2) r = draw(a.seed, genv, a.step, P_OBSNOISE + (stream << 8));
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-    for (int j = 0; j < d; ++j) {
-        float x = black ? 0.0f : v[j];
-        if (a.mode >= 2) x = x * (u01(rr[j]) * a.noise_range + a.noise_lo);
-        v[j] = x;
-    }
-}
 __global__ void sensor_frontend_kernel(const FrontArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -222,11 +204,11 @@ __global__ void sensor_frontend_kernel(const FrontArgs a) {
     }
     acc[2] = acc[2] + 9.8f;                                              // :367
     for (int j = 0; j < 4; ++j) ang[j] = r[3 + j];
-    fault3(a, genv, 1, false, gyr, 3);                                   // :374
-    fault3(a, genv, 3, true, ang, 4);                                    // :383
-    fault3(a, genv, 4, false, acc, 3);                                   // :401
-    fault3(a, genv, 5, false, pos, 3);                                   // :403
-    fault3(a, genv, 6, false, vel, 3);                                   // :404
+    sensor_fault(a.f, genv, 1, false, gyr, 3);                                   // :374
+    sensor_fault(a.f, genv, 3, true, ang, 4);                                    // :383
+    sensor_fault(a.f, genv, 4, false, acc, 3);                                   // :401
+    sensor_fault(a.f, genv, 5, false, pos, 3);                                   // :403
+    sensor_fault(a.f, genv, 6, false, vel, 3);                                   // :404
     float* o = a.sensors + i * 16;
     for (int j = 0; j < 3; ++j) { o[j] = acc[j]; o[3 + j] = gyr[j]; o[10 + j] = pos[j]; o[13 + j] = vel[j]; }
     for (int j = 0; j < 4; ++j) o[6 + j] = ang[j];
@@ -247,19 +229,7 @@ __global__ void waypoint_kernel(int64_t n, const float* __restrict__ root13, con
     const float* r = root13 + i * 13;
     const float p[3] = {r[0], r[1], r[2]}, t[3] = {target3[i * 3], target3[i * 3 + 1], target3[i * 3 + 2]};
     float w[3] = {waypoint3[i * 3], waypoint3[i * 3 + 1], waypoint3[i * 3 + 2]};
-    if (warm) { w[0] = t[0]; w[1] = t[1]; w[2] = t[2]; }                                   // :461-463
-    const float tv[3] = {t[0] - p[0], t[1] - p[1], t[2] - p[2]};
-    const float td = sqrtf((tv[0] * tv[0] + tv[1] * tv[1]) + tv[2] * tv[2]);
-    const float wv[3] = {w[0] - p[0], w[1] - p[1], w[2] - p[2]};
-    const float wd = sqrtf((wv[0] * wv[0] + wv[1] * wv[1]) + wv[2] * wv[2]);
-    if (!warm) {
-        if ((wd < 0.5f || wd > 1.0f) && wd != 0.0f) {                                       // :473-482
-            const float rv[3] = {t[0] - p[0], t[1] - p[1], (t[2] + 0.7f) - p[2]};
-            const float rd = sqrtf((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
-            for (int j = 0; j < 3; ++j) w[j] = (rv[j] / rd) * 0.75f + p[j];
-        }
-        if (td < 0.75f) { w[0] = t[0]; w[1] = t[1]; w[2] = t[2] + 0.09f; }                  // :483-486
-    }
+    waypoint_update(p, t, w, warm != 0);
     for (int j = 0; j < 3; ++j) waypoint3[i * 3 + j] = w[j];
     cmd4[i] = make_float4(w[0], w[1], w[2], 0.0f);                                         // :488
     float* e = est13 + i * 13;
@@ -389,11 +359,11 @@ extern "C" int ozl_sensor_frontend(int64_t n, const float* root13, float* prev_l
     if (!root13 || !prev_linvel3 || !sensors16) return set_error("ozl_sensor_frontend: NULL buffer");
     if (mode < 0 || mode > 3) return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");
     FrontArgs a;
-    a.n = n; a.root13 = root13; a.prev_linvel = prev_linvel3; a.sensors = sensors16; a.dt = dt; a.mode = mode;
-    a.flicker_p = (mode == 3) ? 0.1f : pomdp_prob;
+    a.n = n; a.root13 = root13; a.prev_linvel = prev_linvel3; a.sensors = sensors16; a.dt = dt; a.f.mode = mode;
+    a.f.flicker_p = (mode == 3) ? 0.1f : pomdp_prob;
     const float lo = (float)(1.0 - (double)pomdp_prob), hi = (float)(1.0 + (double)pomdp_prob);
-    a.noise_lo = lo; a.noise_range = hi - lo;
-    a.seed = seed; a.step = step; a.env_id_base = (uint32_t)env_id_base;
+    a.f.noise_lo = lo; a.f.noise_range = hi - lo;
+    a.f.seed = seed; a.f.step = step; a.env_id_base = (uint32_t)env_id_base;
     sensor_frontend_kernel<<<nblk(n, 256), 256, 0, st>>>(a);
     return check_cuda(cudaGetLastError(), "sensor_frontend_kernel");
 }

@@ -1,0 +1,166 @@
+// Fused estimator + controller of the EKFLeeLanded task: ONE kernel per control step, one env per thread, replaces the
+// chain apply_resets -> get_state -> sensor_frontend -> ekf_set_q -> ekf_update -> pv_reset -> pv_step -> waypoint ->
+// lee_wrench (8 launches + AoS gathers).  Reference: isaacgymenvs/tasks/ekf_lee_landed.py:308-530.
+//   * reads the true root state straight from the env handle's SoA planes (no AoS gather); envs flagged for reset are
+//     re-spawned in registers with the same draws ozl_step will make (reset_idx runs first, :312-314)
+//   * the step index, warm-up flag and the shared sensor-trigger counters come from the env's DEVICE step counter, so the
+//     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
+//   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
+#include "internal.h"
+#include "filters.cuh"
+#include "glue.cuh"
+#include "lee_control.cuh"
+
+namespace ozl {
+
+struct EkfLeeArgs {
+    int64_t n;
+    double* ekf_q;  double* ekf_P;        // [4][n], [16][n]
+    float* pv_x;    float* pv_P;          // [9][n], [81][n]
+    float* prev_linvel;                   // [n,3]
+    float* waypoint;                      // [n,3]
+    const float* target;                  // [n,3]
+    const int64_t* reset;                 // [n]
+    float4* wrench;                       // [n] out
+    float* est13;   float4* cmd4;         // optional debug outputs
+    float dt, dt2, mg, hover;
+    int64_t convergence;
+    FaultCfg f;                           // mode / probabilities / seed (step filled in-kernel)
+    uint32_t pos_period, pos_phase, vel_period, vel_phase;
+    int per_env_triggers;
+    float acc_var[3], pos_var[3];
+    double ekf_Dt, ekf_g_noise;
+    LeeGains g;
+};
+
+__global__ void __launch_bounds__(128)
+ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t step = *reinterpret_cast<const volatile unsigned long long*>(pl.ctrl);
+    const bool warm = (int64_t)step < a.convergence;                                     // :339
+    const uint32_t genv = c.env_id_base + (uint32_t)i;
+    const bool rst = a.reset[i] != 0;
+    // ---- true root state (post reset_idx)
+    float p[3], q[4], v[3], w[3];
+    if (rst) {
+        const uint4 r = draw(c.seed, genv, step, P_SPAWN);
+        p[0] = c.spawn_base[0] + (c.spawn_range[0] * u01(r.x) + c.spawn_lo[0]);
+        p[1] = c.spawn_base[1] + (c.spawn_range[1] * u01(r.y) + c.spawn_lo[1]);
+        p[2] = c.spawn_base[2] + (c.spawn_range[2] * u01(r.z) + c.spawn_lo[2]);
+        q[0] = q[1] = q[2] = 0.f; q[3] = 1.f;
+        for (int j = 0; j < 3; ++j) { v[j] = 0.f; w[j] = 0.f; }
+    } else {
+        const float4 d0 = pl.d0[i], d1 = pl.d1[i], d2 = pl.d2[i];
+        const float wz = pl.d3[i].x;
+        p[0] = d0.x; p[1] = d0.y; p[2] = d0.z; q[0] = d0.w; q[1] = d1.x; q[2] = d1.y; q[3] = d1.z;
+        v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz;
+    }
+    // ---- sensor front-end (:345-346,366-375,397-406)
+    FaultCfg f = a.f;
+    f.step = step;
+    if (warm) f.mode = 0;
+    float acc[3], gyr[3], ang[4], pos[3], vel[3];
+    for (int j = 0; j < 3; ++j) {
+        acc[j] = (v[j] - a.prev_linvel[i * 3 + j]) / a.dt;
+        gyr[j] = w[j]; pos[j] = p[j]; vel[j] = v[j];
+        a.prev_linvel[i * 3 + j] = v[j];                                                  // :454
+    }
+    acc[2] = acc[2] + 9.8f;
+    for (int j = 0; j < 4; ++j) ang[j] = q[j];
+    sensor_fault(f, genv, 1, false, gyr, 3);
+    sensor_fault(f, genv, 3, true, ang, 4);
+    sensor_fault(f, genv, 4, false, acc, 3);
+    sensor_fault(f, genv, 5, false, pos, 3);
+    sensor_fault(f, genv, 6, false, vel, 3);
+    // ---- attitude EKF (:348-352,378-391)
+    float q32[4];
+    {
+        EKF4 s;
+        if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
+        else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
+        for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
+        const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
+        const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
+        ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
+        for (int k = 0; k < 4; ++k) { a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
+        for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4];
+    }
+    // ---- PV filter (:353-358,397-444)
+    float est_p[3], est_v[3];
+    {
+        PV s;
+        for (int k = 0; k < 9; ++k) s.x[k] = a.pv_x[(int64_t)k * a.n + i];
+        for (int k = 0; k < 81; ++k) s.P[k / 9][k % 9] = a.pv_P[(int64_t)k * a.n + i];
+        if (rst) { for (int k = 0; k < 3; ++k) { s.x[k] = p[k]; s.x[3 + k] = v[k]; s.x[6 + k] = 0.f; } }
+        const float qt[4] = {q[3], q[0], q[1], q[2]};
+        pv_predict(s, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
+        const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n + (uint64_t)i;   // shared counters (:425-440)
+        if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(s, pos, a.pos_var);
+        const float zero3[3] = {0.f, 0.f, 0.f};
+        if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(s, vel, zero3);  // gps_var=None => R = 0
+        for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = s.x[kk];
+        for (int kk = 0; kk < 81; ++kk) a.pv_P[(int64_t)kk * a.n + i] = s.P[kk / 9][kk % 9];
+        for (int kk = 0; kk < 3; ++kk) { est_p[kk] = s.x[kk]; est_v[kk] = s.x[3 + kk]; }
+    }
+    // ---- waypoint + controller (:458-529)
+    const float t[3] = {a.target[i * 3], a.target[i * 3 + 1], a.target[i * 3 + 2]};
+    float wp[3] = {a.waypoint[i * 3], a.waypoint[i * 3 + 1], a.waypoint[i * 3 + 2]};
+    waypoint_update(p, t, wp, warm);
+    for (int j = 0; j < 3; ++j) a.waypoint[i * 3 + j] = wp[j];
+    const float cmd[4] = {wp[0] * a.g.scale[0], wp[1] * a.g.scale[1], wp[2] * a.g.scale[2], 0.0f};
+    float4 wr;
+    if (warm) {
+        wr = make_float4(a.hover, 0.f, 0.f, 0.f);                                         // :526-528
+    } else {
+        float th, tq[3];
+        lee_control(LEE_POSITION, est_p, q, est_v, w, cmd, a.g, th, tq);                   // :493-499
+        wr = make_float4(a.mg * th, tq[0], tq[1], tq[2]);                                  // :504-505
+    }
+    a.wrench[i] = wr;
+    if (a.est13) {
+        float* e = a.est13 + i * 13;
+        for (int j = 0; j < 3; ++j) { e[j] = warm ? p[j] : est_p[j]; e[7 + j] = warm ? v[j] : est_v[j]; e[10 + j] = w[j]; }
+        for (int j = 0; j < 4; ++j) e[3 + j] = q[j];
+    }
+    if (a.cmd4) a.cmd4[i] = make_float4(wp[0], wp[1], wp[2], 0.0f);
+}
+
+}  // namespace ozl
+
+using namespace ozl;
+
+extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* stream) {
+    if (!env || !in) return set_error("ozl_ekf_lee_step: NULL argument");
+    if (!in->ekf_q4xN || !in->ekf_P16xN || !in->pv_x9xN || !in->pv_P81xN || !in->prev_linvel3 || !in->waypoint3 || !in->target3 ||
+        !in->reset || !in->wrench4 || !in->gains16)
+        return set_error("ozl_ekf_lee_step: NULL buffer");
+    if (((uintptr_t)in->wrench4 & 15) || ((uintptr_t)in->cmd4 & 15)) return set_error("ozl_ekf_lee_step: wrench4/cmd4 must be 16-byte aligned");
+    if (in->pomdp_mode < 0 || in->pomdp_mode > 3) return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");
+    EkfLeeArgs a;
+    a.n = env->cfg.num_envs;
+    a.ekf_q = in->ekf_q4xN; a.ekf_P = in->ekf_P16xN; a.pv_x = in->pv_x9xN; a.pv_P = in->pv_P81xN;
+    a.prev_linvel = in->prev_linvel3; a.waypoint = in->waypoint3; a.target = in->target3; a.reset = in->reset;
+    a.wrench = (float4*)in->wrench4; a.est13 = in->est13; a.cmd4 = (float4*)in->cmd4;
+    a.dt = in->dt; a.dt2 = (float)((double)in->dt * (double)in->dt); a.mg = in->mg; a.hover = in->hover_force;
+    a.convergence = in->convergence_steps;
+    a.f.mode = in->pomdp_mode;
+    a.f.flicker_p = (in->pomdp_mode == 3) ? 0.1f : in->pomdp_prob;
+    const float lo = (float)(1.0 - (double)in->pomdp_prob), hi = (float)(1.0 + (double)in->pomdp_prob);
+    a.f.noise_lo = lo; a.f.noise_range = hi - lo;
+    a.f.seed = env->cfg.seed; a.f.step = 0;
+    a.pos_period = in->pos_period; a.pos_phase = in->pos_phase; a.vel_period = in->vel_period; a.vel_phase = in->vel_phase;
+    a.per_env_triggers = in->per_env_triggers;
+    for (int j = 0; j < 3; ++j) { a.acc_var[j] = in->acc_var[j]; a.pos_var[j] = in->pos_var[j]; }
+    a.ekf_Dt = in->ekf_Dt; a.ekf_g_noise = in->ekf_g_noise;
+    for (int k = 0; k < 3; ++k) { a.g.kP[k] = in->gains16[k]; a.g.kV[k] = in->gains16[3 + k]; a.g.kR[k] = in->gains16[6 + k]; a.g.kO[k] = in->gains16[9 + k]; }
+    for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
+    ekf_lee_fused_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a);
+    return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
+}
+
+extern "C" int ozl_step_counter_ptr(ozl_env* env, const uint64_t** out) {
+    if (!env || !out) return set_error("ozl_step_counter_ptr: NULL argument");
+    *out = reinterpret_cast<const uint64_t*>(env->pl.ctrl);
+    return 0;
+}

@@ -25,6 +25,7 @@ struct HuskyArgs {
     float* wheels;           // [n,4] right,left,right,left (may be null)
     float* target3;          // [n,3] landing target riding on the vehicle
     uint64_t seed, step;
+    const unsigned long long* step_ptr;
     uint32_t env_id_base;
     float dt, thresh, kp_lin, kp_ang, ang_thresh, x_offset, target_z, respawn_limit;
 };
@@ -62,11 +63,12 @@ husky_step_kernel(const HuskyArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const uint32_t genv = a.env_id_base + (uint32_t)i;
+    const uint64_t step = a.step_ptr ? *reinterpret_cast<const volatile unsigned long long*>(a.step_ptr) : a.step;
     float4 p = a.pose[i];
     int2 id = a.idx[i];
     // re-spawn a strayed vehicle when its drone resets (landing.py:263-270)
     if (a.reset && a.reset[i] != 0 && (fabsf(p.x) > a.respawn_limit || fabsf(p.y) > a.respawn_limit)) {
-        const uint4 r = draw(a.seed, genv, a.step, P_HUSKY + 1);
+        const uint4 r = draw(a.seed, genv, step, P_HUSKY + 1);
         p.x = 3.0f * u01(r.x) + -1.5f;
         p.y = 3.0f * u01(r.y) + -1.5f;
         p.z = 0.0f;
@@ -76,7 +78,7 @@ husky_step_kernel(const HuskyArgs a) {
     float dx = tgt.x - p.x, dy = tgt.y - p.y;
     if (sqrtf(dx * dx + dy * dy) < a.thresh) id.y += 1;                       // :339-343
     if (id.y == kNumWaypoints || (id.x == 2 && id.y > 3)) {                   // :235-238
-        redraw(a, genv, a.step, id.x, p.w);
+        redraw(a, genv, step, id.x, p.w);
         id.y = 0;
     }
     tgt = lookup(a, id.x, id.y, p.w);
@@ -119,7 +121,7 @@ static int fill(const ozl_husky_args* in, HuskyArgs& a, const char* who) {
     if (((uintptr_t)in->pose4 & 15) || ((uintptr_t)in->wheels4 & 15)) return set_error("%s: pose4/wheels4 must be 16-byte aligned", who);
     a.n = in->n; a.pose = (float4*)in->pose4; a.idx = (int2*)in->idx2; a.tables = (const float2*)in->tables204x2;
     a.reset = in->reset; a.wheels = in->wheels4; a.target3 = in->target3;
-    a.seed = in->seed; a.step = in->step; a.env_id_base = (uint32_t)in->env_id_base;
+    a.seed = in->seed; a.step = in->step; a.step_ptr = (const unsigned long long*)in->step_ptr; a.env_id_base = (uint32_t)in->env_id_base;
     a.dt = in->dt; a.thresh = in->dist_thresh; a.kp_lin = in->kp_lin; a.kp_ang = in->kp_ang; a.ang_thresh = in->ang_thresh;
     a.x_offset = in->x_offset; a.target_z = in->target_z; a.respawn_limit = in->respawn_limit;
     return 0;

@@ -1,0 +1,92 @@
+"""Rollout collection for the recurrent trainers (BASELINE config 5): env kernels + a torch LSTM policy.
+
+The policy side is deliberately plain PyTorch (a library consumer, like the reference's trainers); what this module
+contributes is the collection LOOP of isaacgymenvs/RPO-LSTM/main.py:89-112 without its host round trips:
+  * `envs.step` is one kernel launch; the sensor-fault wrapper is one more (ouzelum_b200.pomdp.POMDPWrapper);
+  * episode statistics come from the env's metrics vector instead of the O(N) Python scan with `.item()` (main.py:105-110).
+`RecurrentActor` has the architecture of isaacgymenvs/RPO-LSTM/model.py:11-68 (MLP 13->512->256 tanh, LSTM 256->128,
+mean head 128->4, state-independent log-std, RPO mean perturbation U(-alpha, alpha) at update time) with any num_envs and
+device (the reference hard-codes "cuda:0", model.py:65, and reshape(16, 4096), agent.py:61).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+
+def _ortho(layer, gain=math.sqrt(2.0)):
+    nn.init.orthogonal_(layer.weight, gain)
+    nn.init.zeros_(layer.bias)
+    return layer
+
+
+class RecurrentActor(nn.Module):
+    def __init__(self, num_obs=13, num_actions=4, rpo_alpha=0.5):
+        super().__init__()
+        self.rpo_alpha = rpo_alpha
+        self.network = nn.Sequential(_ortho(nn.Linear(num_obs, 512)), nn.Tanh(), _ortho(nn.Linear(512, 256)), nn.Tanh())
+        self.lstm = nn.LSTM(256, 128)
+        for name, p in self.lstm.named_parameters():
+            nn.init.zeros_(p) if "bias" in name else nn.init.orthogonal_(p, 1.0)
+        self.actor_mean = _ortho(nn.Linear(128, num_actions), gain=0.01)
+        self.actor_logstd = nn.Parameter(torch.zeros(1, num_actions))
+
+    def initial_state(self, num_envs, device):
+        z = torch.zeros(self.lstm.num_layers, num_envs, self.lstm.hidden_size, device=device)
+        return z, z.clone()
+
+    def forward(self, obs, lstm_state, done, action=None):
+        """One time step for every env (the collection path of model.py:35-68)."""
+        x = self.network(obs)
+        keep = (1.0 - done).view(-1, 1)
+        h0, c0 = keep * lstm_state[0][0], keep * lstm_state[1][0]
+        # single-step LSTM cell written as two GEMMs + pointwise on the nn.LSTM's own parameters: cuDNN's persistent RNN
+        # kernel needs 8.4 ms for (seq 1, batch 32768, hidden 128) on B200, the GEMM form 0.2 ms (profiles/r01_configs.md)
+        L = self.lstm
+        gates = torch.addmm(L.bias_ih_l0 + L.bias_hh_l0, x, L.weight_ih_l0.t()).addmm_(h0, L.weight_hh_l0.t())
+        i, f, g, o = gates.chunk(4, dim=1)
+        c1 = torch.sigmoid(f) * c0 + torch.sigmoid(i) * torch.tanh(g)
+        h1 = torch.sigmoid(o) * torch.tanh(c1)
+        lstm_state = (h1.unsqueeze(0), c1.unsqueeze(0))
+        mean = self.actor_mean(h1)
+        std = torch.exp(self.actor_logstd.expand_as(mean))
+        if action is None:
+            action = mean + std * torch.randn_like(mean)
+        else:
+            mean = mean + (torch.rand_like(mean) * 2 - 1) * self.rpo_alpha
+        logp = (-((action - mean) ** 2) / (2 * std * std) - torch.log(std) - 0.5 * math.log(2 * math.pi)).sum(1)
+        return action, logp, lstm_state
+
+
+class RolloutStorage:
+    """The buffers of main.py:70-78 for any (rollout_steps, num_envs)."""
+
+    def __init__(self, steps, num_envs, num_obs, num_actions, device):
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        self.obs, self.pomdps = z(steps, num_envs, num_obs), z(steps, num_envs, num_obs)
+        self.actions, self.logprobs = z(steps, num_envs, num_actions), z(steps, num_envs)
+        self.rewards, self.dones = z(steps, num_envs), z(steps, num_envs)
+
+
+@torch.no_grad()
+def collect_rollout(env, actor, storage, state, pomdp=None):
+    """One `rollout_steps` collection pass (main.py:91-103).  `state` = dict(next_obs, pomdp_obs, next_done, lstm_state)
+    carried between calls.  Returns the updated state; env-side episode statistics accumulate in `env.metrics()`."""
+    steps = storage.obs.shape[0]
+    next_obs, pomdp_obs, next_done, lstm_state = state["next_obs"], state["pomdp_obs"], state["next_done"], state["lstm_state"]
+    for t in range(steps):
+        storage.obs[t], storage.pomdps[t], storage.dones[t] = next_obs, pomdp_obs, next_done
+        action, logp, lstm_state = actor(pomdp_obs, lstm_state, next_done)
+        storage.actions[t], storage.logprobs[t] = action, logp
+        obs_dict, rew, done, _ = env.step(action)
+        next_obs = obs_dict["obs"]
+        storage.rewards[t] = rew
+        next_done = done.to(torch.float32)
+        pomdp_obs = pomdp.observation(next_obs) if pomdp is not None else next_obs
+    return dict(next_obs=next_obs, pomdp_obs=pomdp_obs, next_done=next_done, lstm_state=lstm_state)
+
+
+def initial_rollout_state(env, actor):
+    obs = env.reset()["obs"]
+    return dict(next_obs=obs, pomdp_obs=obs.clone(), next_done=torch.zeros(env.num_envs, device=obs.device),
+                lstm_state=actor.initial_state(env.num_envs, obs.device))

@@ -41,6 +41,7 @@ class EKFLeeLanded(_VehicleTargetTask):
         self._pomdp_mode = _POMDP[env.get("POMDP", "none")]
         self._pomdp_prob = float(env.get("pomdp_prob", 0.0))
         self.per_env_triggers = bool(env.get("perEnvSensorTriggers", False))
+        self.fused = bool(env.get("fusedEstimator", True))      # one kernel for the whole estimator + controller chain
         super().__init__(cfg, *a, **k)
 
     def _native_cfg(self):
@@ -67,6 +68,28 @@ class EKFLeeLanded(_VehicleTargetTask):
         # shared trigger counters (ekf_lee_landed.py:153-154,425-440) => fix iff (step*N + env) % period == phase
         self._trigger = self._trigger_rule()
         self._seed, self._base = int(self.cfg["env"].get("seed", 0)), int(self.cfg["env"].get("envIdBase", 0))
+        # fused path: argument block of ozl_ekf_lee_step (all pointers are fixed => the step is CUDA-graph capturable)
+        import ctypes as C
+        from .._lib import OzlEkfLeeArgs
+        a = self._fa = OzlEkfLeeArgs()
+        a.ekf_q4xN, a.ekf_P16xN = self.ekf._q.data_ptr(), self.ekf._P.data_ptr()
+        a.pv_x9xN, a.pv_P81xN = self.pvfilters._x.data_ptr(), self.pvfilters._P.data_ptr()
+        a.prev_linvel3, a.waypoint3 = self.prev_root_linvels.data_ptr(), self.target_waypoints.data_ptr()
+        a.target3, a.reset, a.wrench4 = self.husky.target.data_ptr(), self.reset_buf.data_ptr() if hasattr(self, "reset_buf") else 0, self._wrench.data_ptr()
+        a.est13, a.cmd4, a.gains16 = self._est.data_ptr(), self._cmd.data_ptr(), self.controller._gains
+        a.dt, a.mg, a.hover_force = self.dt, self.mg, float(self._hover[0, 0].item())
+        a.convergence_steps = int(self.ConvergenceTime)
+        a.pomdp_mode, a.pomdp_prob = self._pomdp_mode, self._pomdp_prob
+        pp, ph, vp, vh = (1, 0, 1, 0) if self.per_env_triggers else self._trigger
+        a.pos_period, a.pos_phase = (pp if self.attach_pos_sensor else 0), ph
+        a.vel_period, a.vel_phase = (vp if self.attach_vel_sensor else 0), vh
+        a.per_env_triggers = 1 if self.per_env_triggers else 0
+        a.acc_var[:] = [1.0, 1.0, 1.0]
+        a.pos_var[:] = [0.0000001] * 3
+        a.ekf_Dt, a.ekf_g_noise = float(self.ekf.Dt), float(self.ekf.g_noise)
+        ctr = C.c_void_p()
+        check(lib.ozl_step_counter_ptr(self.sim._h, C.byref(ctr)))
+        self.husky.follow_step_counter(ctr.value)
 
     def _trigger_rule(self):
         def rule(freq, count0, attached):
@@ -84,6 +107,21 @@ class EKFLeeLanded(_VehicleTargetTask):
         return pp, ph, vp, vh
 
     def _launch(self, actions):
+        if self.fused:
+            return self._launch_fused()
+        return self._launch_chain()
+
+    def _launch_fused(self):
+        """vehicle kernel -> fused estimator+controller kernel -> step kernel: three launches, no host-changing arguments."""
+        import ctypes as C
+        self._fa.reset = self.reset_buf.data_ptr()
+        self._target = self.husky.step(self.reset_buf)
+        check(lib.ozl_ekf_lee_step(self.sim._h, C.byref(self._fa), torch.cuda.current_stream().cuda_stream))
+        self.sim.step_wrench(self._wrench, self._target, self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf,
+                             self._timeout_u8, self.episode_return_buf)
+        self.sim_step_count += 1
+
+    def _launch_chain(self):
         s = torch.cuda.current_stream().cuda_stream
         n = self.num_envs
         warm = self.sim_step_count < self.ConvergenceTime                              # :339

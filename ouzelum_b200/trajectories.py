@@ -76,6 +76,11 @@ class HuskyFollower:
     def target_indices(self):
         return self.idx[:, 1]
 
+    def follow_step_counter(self, device_ptr):
+        """Read the step index from a device counter (ozl_step_counter_ptr) instead of the host-side count: makes the
+        launch free of host-changing arguments (CUDA-graph capturable)."""
+        self._a.step_ptr = device_ptr
+
     def step(self, reset_buf=None):
         """Advance every vehicle one control step; returns the landing target [N,3] riding on it."""
         a = self._a

@@ -131,3 +131,20 @@ def test_task_config_mirrors_yaml():
     from ouzelum_b200.spaces import Box
     b = Box(np.ones(4) * -1.0, np.ones(4) * 1.0)
     assert b.shape == (4,) and b.contains(b.sample())
+
+
+def test_recurrent_actor_cell_equals_nn_lstm():
+    """The GEMM-form single-step LSTM cell of the rollout policy equals nn.LSTM on the same parameters (CPU, torch only)."""
+    import torch
+    from ouzelum_b200.rollout import RecurrentActor
+    torch.manual_seed(0)
+    a = RecurrentActor()
+    n = 64
+    obs, done = torch.randn(n, 13), (torch.rand(n) < 0.3).float()
+    st = (torch.randn(1, n, 128), torch.randn(1, n, 128))
+    with torch.no_grad():
+        act, logp, s1 = a(obs, st, done)
+        keep = (1 - done).view(1, -1, 1)
+        _, s2 = a.lstm(a.network(obs).unsqueeze(0), (keep * st[0], keep * st[1]))
+    assert act.shape == (n, 4) and logp.shape == (n,)
+    assert (s1[0] - s2[0]).abs().max() < 1e-5 and (s1[1] - s2[1]).abs().max() < 1e-5

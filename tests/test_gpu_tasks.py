@@ -199,7 +199,7 @@ def test_ekf_lee_landed_glue_vs_oracle(pomdp):
     from oracle.ekf_lee_landed import EKFLeeGlue
     n, conv = 96, 6
     cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=4, ConvergenceTime=conv, POMDP=pomdp, pomdp_prob=0.05,
-                                   maxEpisodeLength=25)
+                                   maxEpisodeLength=25, fusedEstimator=False)
     env = ouzelum_b200.make(seed=4, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
     mode = {"none": 0, "random_noise": 2}[pomdp]
     ora = EKFLeeGlue(n, convergence=conv, pomdp_mode=mode, pomdp_prob=0.05, seed=4)
@@ -267,3 +267,26 @@ def test_step_host_zero_copy_matches_device_step():
     assert torch.equal(e1.reset_buf, e2.reset_buf) and torch.equal(e1.progress_buf, e2.progress_buf)
     with pytest.raises(ValueError):
         e2.step_host(torch.zeros(n, 4))          # not pinned
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_ekf_lee_fused_kernel_equals_kernel_chain(graph):
+    """The single fused estimator+controller kernel (ozl_ekf_lee_step) against the 9-launch chain of stand-alone kernels
+    (each of which is tested against the oracle): same filters, waypoints, wrench and env outputs, bit for bit."""
+    import ouzelum_b200
+    n = 777
+    mk = lambda fused: ouzelum_b200.make(seed=6, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                         cfg=ouzelum_b200.task_config("EKFLeeLanded", n, seed=6, ConvergenceTime=7, POMDP="flickering_and_random_noise",
+                                                                      pomdp_prob=0.1, maxEpisodeLength=30, fusedEstimator=fused,
+                                                                      useCudaGraph=(graph and fused)))
+    e1, e2 = mk(False), mk(True)
+    a = torch.zeros(n, 4, device=DEV)
+    for t in range(70):
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        assert torch.equal(e1._wrench if t >= 7 else e1._hover, e2._wrench), t
+        assert torch.equal(e1.ekf._q, e2.ekf._q) and torch.equal(e1.ekf._P, e2.ekf._P), t
+        assert torch.equal(e1.pvfilters._x, e2.pvfilters._x) and torch.equal(e1.pvfilters._P, e2.pvfilters._P), t
+        assert torch.equal(e1.target_waypoints, e2.target_waypoints), t
+        assert torch.equal(o1["obs"], o2["obs"]) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert e1.episodes == e2.episodes and e1.episodes > 0
