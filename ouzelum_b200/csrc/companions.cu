@@ -172,7 +172,7 @@ __global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float 
         const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
         for (int j = 0; j < 4 && j0 + j < d; ++j) {
             float v = blackout ? 0.0f : in[i * d + j0 + j];
-            if (mode >= 2) v = v * (u01(rr[j]) * noise_range + noise_lo);
+            if (mode >= 2) v = __fmul_rn(v, __fadd_rn(__fmul_rn(u01(rr[j]), noise_range), noise_lo));   // no FMA: bit-exact vs oracle
             out[i * d + j0 + j] = v;
         }
     }

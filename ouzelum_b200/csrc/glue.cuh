@@ -26,7 +26,9 @@ __device__ __forceinline__ void sensor_fault(const FaultCfg& a, uint32_t genv, u
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
     for (int j = 0; j < d; ++j) {
         float x = black ? 0.0f : v[j];
-        if (a.mode >= 2) x = x * (u01(rr[j]) * a.noise_range + a.noise_lo);
+        // explicit _rn intrinsics: never contracted to FMA, so the noise factor is bit-identical to the oracle's and to the
+        // in-kernel observation noise of quad_step (this TU is compiled with FMA contraction on)
+        if (a.mode >= 2) x = __fmul_rn(x, __fadd_rn(__fmul_rn(u01(rr[j]), a.noise_range), a.noise_lo));
         v[j] = x;
     }
 }
