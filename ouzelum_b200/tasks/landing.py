@@ -83,3 +83,40 @@ class Landed(_VehicleTargetTask):
     def landings(self):
         """Episodes that ended after the vehicle was reached (the reference writes this to metrics/<pomdp>_<p>.txt)."""
         return int(self.sim.metrics()[2].item())
+
+    # ---- on-disk formats of the reference's evaluation runs (opt-in: they cost a host sync per step) ----------------
+    def enable_logging(self, log_dir):
+        """Reproduce the files `Landed` writes (landed.py:114-117,265-271,346-353):
+          <log_dir>/trajectories/<pomdp>_<prob>_ep_<k>.csv   one row per step: drone x,y,z, target x,y,z of env 0
+                                                            (ep_0 starts with the header 'Position X,Position Y,Position Z')
+          <log_dir>/metrics/<pomdp>_<prob>.txt               running count of episodes that ended after a landing
+        so the MATLAB plotting scripts (isaacgymenvs/trajectories/csvreadf.m) keep working."""
+        import csv
+        import os
+        self._log_dir = log_dir
+        self._csv = csv
+        env = self.cfg["env"]
+        self._log_tag = f"{env.get('POMDP', 'flicker')}_{env.get('pomdp_prob', 0.01)}"
+        os.makedirs(os.path.join(log_dir, "trajectories"), exist_ok=True)
+        os.makedirs(os.path.join(log_dir, "metrics"), exist_ok=True)
+        self.epi = 0
+        with open(self._traj_path(), "w") as f:
+            csv.writer(f).writerow(["Position X", "Position Y", "Position Z"])
+
+    def _traj_path(self):
+        import os
+        return os.path.join(self._log_dir, "trajectories", f"{self._log_tag}_ep_{self.epi}.csv")
+
+    def _launch(self, actions):
+        log = getattr(self, "_log_dir", None)
+        if log and bool(self.reset_buf[0].item()):                 # pre_physics_step: env 0 is being reset (landed.py:262-264)
+            self.epi += 1
+        super()._launch(actions)
+        if log:
+            import os
+            st = self.sim.get_state()
+            row = torch.cat([st["root"][0, 0:3], st["target"][0]]).cpu().tolist()          # landed.py:342-353
+            with open(self._traj_path(), "a") as f:
+                self._csv.writer(f).writerow(row)
+            with open(os.path.join(log, "metrics", f"{self._log_tag}.txt"), "w") as f:      # landed.py:269-271
+                f.write(str(self.landings))

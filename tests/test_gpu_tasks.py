@@ -306,3 +306,21 @@ def test_ekf_lee_fused_kernel_equals_kernel_chain(graph):
         flips += int((d1 != d2).sum())
     assert flips <= 2, flips                      # a reset decided within rounding distance of a threshold
     assert e1.episodes > 0 and abs(e1.episodes - e2.episodes) <= 2
+
+
+def test_landed_writes_reference_log_formats(tmp_path):
+    """On-disk formats of the reference's evaluation runs (landed.py:114-117,265-271,346-353)."""
+    import csv
+    import ouzelum_b200
+    cfg = ouzelum_b200.task_config("Landed", 1, seed=2, maxEpisodeLength=40, pomdp_prob=0.01)
+    env = ouzelum_b200.make(seed=2, task="Landed", num_envs=1, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
+    env.enable_logging(str(tmp_path))
+    for _ in range(100):
+        env.step(torch.zeros(1, 4, device=DEV))
+    files = sorted((tmp_path / "trajectories").iterdir())
+    assert (tmp_path / "trajectories" / "flicker_0.01_ep_0.csv").read_text().splitlines() == ["Position X,Position Y,Position Z"]
+    assert len(files) >= 3
+    rows = list(csv.reader(open(tmp_path / "trajectories" / "flicker_0.01_ep_1.csv")))
+    assert all(len(r) == 6 for r in rows) and abs(float(rows[0][5]) - 0.377) < 1e-6          # target z == 0.377 (landed.py:78)
+    assert abs(float(rows[0][0])) <= 1.51 and 0.7 <= float(rows[0][2]) <= 2.6               # spawn ranges (landed.py:232-235)
+    assert int((tmp_path / "metrics" / "flicker_0.01.txt").read_text()) == env.landings
