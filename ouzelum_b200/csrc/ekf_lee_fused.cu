@@ -51,8 +51,8 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a) {
         q[0] = q[1] = q[2] = 0.f; q[3] = 1.f;
         for (int j = 0; j < 3; ++j) { v[j] = 0.f; w[j] = 0.f; }
     } else {
-        const float4 d0 = pl.d0[i], d1 = pl.d1[i], d2 = pl.d2[i];
-        const float wz = pl.d3[i].x;
+        const float4 d0 = *plane4_ptr(pl, 0, i), d1 = *plane4_ptr(pl, 1, i), d2 = *plane4_ptr(pl, 2, i);
+        const float wz = plane4_ptr(pl, 3, i)->x;
         p[0] = d0.x; p[1] = d0.y; p[2] = d0.z; q[0] = d0.w; q[1] = d1.x; q[2] = d1.y; q[3] = d1.z;
         v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz;
     }

@@ -13,18 +13,44 @@ int check_cuda(cudaError_t e, const char* what);
 constexpr int kMetricSlots = 32;       // metric accumulators are striped over 32 slots (256 B apart) to spread L2 atomics
 constexpr int kMetricStride = 32;      // doubles per slot (16 used)
 
-// Private SoA state of one handle.  Planes are float4-packed so one env == one 16-byte lane per plane
-// and a warp touches 512 contiguous bytes per plane.
+// Private state of one handle: float4-packed planes, so one env == one 16-byte lane per plane.
 //   dynamic (read+written every step):  d0 {px,py,pz,qx} d1 {qy,qz,qw,vx} d2 {vy,vz,wx,wy} d3 {wz,T0,T1,T2} d4 {T3,ep_ret}
 //   static  (read every step, written only on reset/resample):
 //           s0 {tx,ty,tz,fault_eff} s1 {1/mass,ixx,iyy,izz} s2 {arm,thrust_scale,fault_word,mass}
+// Layout (OZL_TILED=1, default): tiles of kTile = 128 envs; inside a tile the planes are stored back to back
+//   [d0 2 KiB][d1][d2][d3][d4 1 KiB][s0 2 KiB][s1][s2]  = 15360 bytes per tile
+// so the CTA that owns a tile reads ONE contiguous 15 KiB region and writes ONE contiguous 9 KiB region (long DRAM bursts,
+// 2 streams per CTA instead of 16), while a warp still touches 512 contiguous bytes per plane.
+// OZL_TILED=0 is the plain plane-major SoA ([plane][N]) kept for A/B measurements.
+#ifndef OZL_TILED
+#define OZL_TILED 1
+#endif
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * (7 * 16 + 8);
 struct Planes {
-    float4 *d0, *d1, *d2, *d3;
-    float2* d4;
-    float4 *s0, *s1, *s2;
-    unsigned long long* ctrl;   // [0] step counter, [1] block ticket
+    char* base;                 // arena
+    int64_t plane4, plane2;     // OZL_TILED=0: byte strides of the float4 / float2 planes
+    unsigned long long* ctrl;   // [0] step counter, [1] block ticket, [2] TMA-kernel tile scheduler, [3] TMA-kernel CTAs done
     double* metrics;            // kMetricSlots x kMetricStride
 };
+// k = 0..3: d0..d3, k = 4..6: s0..s2
+__device__ __forceinline__ float4* plane4_ptr(const Planes& pl, int k, int64_t i) {
+#if OZL_TILED
+    const int64_t tile = i >> 7;
+    const int lane = (int)(i & (kTile - 1));
+    const int off = (k < 4 ? k * 2048 : 9216 + (k - 4) * 2048);
+    return reinterpret_cast<float4*>(pl.base + tile * kTileBytes + off) + lane;
+#else
+    return reinterpret_cast<float4*>(pl.base + (int64_t)k * pl.plane4) + i;
+#endif
+}
+__device__ __forceinline__ float2* plane2_ptr(const Planes& pl, int64_t i) {
+#if OZL_TILED
+    return reinterpret_cast<float2*>(pl.base + (i >> 7) * kTileBytes + 8192) + (int)(i & (kTile - 1));
+#else
+    return reinterpret_cast<float2*>(pl.base + 7 * pl.plane4) + i;
+#endif
+}
 
 }  // namespace ozl
 
@@ -34,6 +60,7 @@ struct ozl_env {
     ozl::Planes pl;
     int device;
     int sm_count;
+    long long tma_min_tiles;    // >= this many whole tiles: use the persistent TMA-pipelined step kernel
     void* arena;                // single cudaMalloc backing all planes
     size_t arena_bytes;
 };

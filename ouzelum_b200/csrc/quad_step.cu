@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include "internal.h"
 
@@ -40,20 +41,21 @@ __device__ __forceinline__ void unpack(const Loaded& L, Env& e) {
     e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z); e.mass = L.s2.w;
 }
 __device__ __forceinline__ void load_env(const Planes& pl, int64_t i, Loaded& L) {
-    L.d0 = pl.d0[i]; L.d1 = pl.d1[i]; L.d2 = pl.d2[i]; L.d3 = pl.d3[i]; L.d4 = pl.d4[i];
-    L.s0 = pl.s0[i]; L.s1 = pl.s1[i]; L.s2 = pl.s2[i];
+    L.d0 = *plane4_ptr(pl, 0, i); L.d1 = *plane4_ptr(pl, 1, i); L.d2 = *plane4_ptr(pl, 2, i); L.d3 = *plane4_ptr(pl, 3, i);
+    L.d4 = *plane2_ptr(pl, i);
+    L.s0 = *plane4_ptr(pl, 4, i); L.s1 = *plane4_ptr(pl, 5, i); L.s2 = *plane4_ptr(pl, 6, i);
 }
 __device__ __forceinline__ void store_dynamic(const Planes& pl, int64_t i, const Env& e) {
-    pl.d0[i] = make_float4(e.p[0], e.p[1], e.p[2], e.q[0]);
-    pl.d1[i] = make_float4(e.q[1], e.q[2], e.q[3], e.v[0]);
-    pl.d2[i] = make_float4(e.v[1], e.v[2], e.w[0], e.w[1]);
-    pl.d3[i] = make_float4(e.w[2], e.T[0], e.T[1], e.T[2]);
-    pl.d4[i] = make_float2(e.T[3], e.ep_ret);
+    *plane4_ptr(pl, 0, i) = make_float4(e.p[0], e.p[1], e.p[2], e.q[0]);
+    *plane4_ptr(pl, 1, i) = make_float4(e.q[1], e.q[2], e.q[3], e.v[0]);
+    *plane4_ptr(pl, 2, i) = make_float4(e.v[1], e.v[2], e.w[0], e.w[1]);
+    *plane4_ptr(pl, 3, i) = make_float4(e.w[2], e.T[0], e.T[1], e.T[2]);
+    *plane2_ptr(pl, i) = make_float2(e.T[3], e.ep_ret);
 }
 __device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const Env& e) {
-    pl.s0[i] = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
-    pl.s1[i] = make_float4(e.inv_m, e.ixx, e.iyy, e.izz);
-    pl.s2[i] = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
+    *plane4_ptr(pl, 4, i) = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
+    *plane4_ptr(pl, 5, i) = make_float4(e.inv_m, e.ixx, e.iyy, e.izz);
+    *plane4_ptr(pl, 6, i) = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
 }
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
@@ -137,11 +139,11 @@ __global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
 quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
-                 const int act_mode, uint8_t* __restrict__ done_u8, const int obs_bulk) {
+                 const int act_mode, uint8_t* __restrict__ done_u8, const int obs_bulk, const int64_t env0) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
     __shared__ double s_m[BLOCK / 32][11];
 
-    const int64_t base = (int64_t)blockIdx.x * BLOCK;
+    const int64_t base = env0 + (int64_t)blockIdx.x * BLOCK;
     const int64_t i = base + threadIdx.x;
     const bool valid = i < c.num_envs;
     const uint64_t step = ld_relaxed(pl.ctrl);
@@ -221,6 +223,176 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
 #if OZL_OBS_BULK
     if (threadIdx.x == 0) bulk_wait_read_all();   // s_obs must stay alive until the bulk copy has read it
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------ K1, TMA-pipelined
+// Persistent variant for large N (rotor-action mode, stored target): one CTA per (SM x 8) slot loops over tiles of
+// kTile = 128 envs.  Thanks to the tiled state layout a tile's whole state is ONE contiguous 15 KiB region, so thread 0
+// brings a tile in with four TMA bulk copies (state, actions, progress, reset -> shared memory, completion on an mbarrier)
+// and issues the loads of tile t+1 as soon as every thread has copied tile t from shared memory into registers: the load
+// latency of the next tile is hidden behind the ~1100-instruction step of the current one regardless of occupancy.
+// Stores stay plain coalesced STG (fire and forget); the [128,13] observation tile leaves through a TMA bulk store.
+// Metrics are accumulated in registers over all tiles of the CTA and reduced once.
+// SASS evidence: UBLKCP (bulk copies), SYNCS (mbarrier).
+constexpr int kTmaStateBytes = kTileBytes;                        // 15360
+constexpr int kTmaActOff = kTmaStateBytes;                        // actions  [128] float4   2048 B
+constexpr int kTmaProgOff = kTmaActOff + kTile * 16;              // progress [128] int64    1024 B
+constexpr int kTmaRstOff = kTmaProgOff + kTile * 8;               // reset    [128] int64    1024 B
+constexpr int kTmaStageBytes = kTmaRstOff + kTile * 8;            // 19456
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#ifndef OZL_TMA_MINB
+#define OZL_TMA_MINB 5
+#endif
+__global__ void __launch_bounds__(kTile, OZL_TMA_MINB)
+quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
+                     float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
+                     uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const int64_t full_tiles,
+                     const int do_ticket) {
+    __shared__ __align__(128) unsigned char s_stage[kTmaStageBytes];
+    __shared__ __align__(16) float s_obs[kTile * 13];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_m[kTile / 32][11];
+    const int tid = threadIdx.x;
+    const uint64_t step = ld_relaxed(pl.ctrl);
+    const bool blackout = flicker_blackout(step, c);
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+
+    auto issue = [&](int64_t tile) {            // thread 0 only
+        mbar_expect_tx(&s_bar, kTmaStageBytes);
+        bulk_load_g2s(s_stage, pl.base + tile * kTileBytes, kTmaStateBytes, &s_bar);
+        bulk_load_g2s(s_stage + kTmaActOff, actions + tile * kTile, kTile * 16, &s_bar);
+        bulk_load_g2s(s_stage + kTmaProgOff, progress + tile * kTile, kTile * 8, &s_bar);
+        bulk_load_g2s(s_stage + kTmaRstOff, reset + tile * kTile, kTile * 8, &s_bar);
+    };
+    // dynamic tile scheduler: the first tile of a CTA is its block index, further tiles come from a device counter (ctrl[2]);
+    // thread 0 requests the index one iteration ahead so the atomic's round trip never sits on the critical path
+    __shared__ long long s_next;
+    int64_t tile = blockIdx.x;
+    long long nxt = 0;
+    if (tid == 0) {
+        if (tile < full_tiles) issue(tile);
+        nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 2, 1ull);
+    }
+
+    // metric accumulators over all tiles of this CTA (small counts packed 8 bits each: a CTA handles far fewer than 255 tiles)
+    double m_rew = 0.0, m_ret = 0.0;
+    int m_len = 0;
+    uint32_t m_pk0 = 0, m_pk1 = 0;      // pk0: done | timeout | crash_dist | crash_z ; pk1: fault_active | resets | landed | tiles
+    uint32_t phase = 0;
+    while (tile < full_tiles) {
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        // shared -> registers (LDS.128, conflict-free: consecutive lanes, 16-byte stride)
+        Loaded L;
+        const float4* s4 = reinterpret_cast<const float4*>(s_stage);
+        L.d0 = s4[tid]; L.d1 = s4[128 + tid]; L.d2 = s4[256 + tid]; L.d3 = s4[384 + tid];
+        L.d4 = reinterpret_cast<const float2*>(s_stage + 8192)[tid];
+        L.s0 = s4[576 + tid]; L.s1 = s4[704 + tid]; L.s2 = s4[832 + tid];
+        const float4 a4 = reinterpret_cast<const float4*>(s_stage + kTmaActOff)[tid];
+        const int64_t prog = reinterpret_cast<const int64_t*>(s_stage + kTmaProgOff)[tid];
+        const bool rst = reinterpret_cast<const int64_t*>(s_stage + kTmaRstOff)[tid] != 0;
+        if (tid == 0) {
+            bulk_wait_read_all();                // previous tile's observation store has finished reading s_obs
+            s_next = nxt;
+        }
+        __syncthreads();                         // everyone has copied the stage out, s_obs is free, s_next is published
+        const int64_t next = s_next;
+        if (tid == 0) {
+            if (next < full_tiles) {
+                issue(next);
+                nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 2, 1ull);
+            }
+        }
+
+        const int64_t i = tile * kTile + tid;
+        Env e;
+        unpack(L, e);
+        const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+        const uint32_t genv = c.env_id_base + (uint32_t)i;
+        StepOut o;
+        env_step(e, act, prog, rst, genv, step, c, o, ACT_ROTORS, nullptr);
+        obs_epilogue(o.obs, genv, step, blackout, c);
+        store_dynamic(pl, i, e);
+        if (o.static_dirty) store_static(pl, i, e);
+        rew[i] = o.rew;
+        reset[i] = o.reset ? 1 : 0;
+        progress[i] = o.prog;
+        if (timeout) timeout[i] = o.timeout ? 1 : 0;
+        if (ep_ret_out) ep_ret_out[i] = o.ep_ret_done;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) s_obs[tid * 13 + j] = o.obs[j];
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) bulk_store_s2g(obs + tile * (kTile * 13), s_obs, kTile * 13 * 4);
+        // metrics
+        m_rew += (double)o.rew;
+        if (o.reset) { m_ret += (double)o.ep_ret_done; m_len += (int)o.prog; }
+        m_pk0 += (uint32_t)o.reset | ((uint32_t)o.timeout << 8) | ((uint32_t)o.crash_dist << 16) | ((uint32_t)o.crash_z << 24);
+        m_pk1 += (uint32_t)o.fault_active | ((uint32_t)o.did_reset << 8) | ((uint32_t)o.landed_episode << 16) | (1u << 24);
+        tile = next;
+    }
+    const int m_done = m_pk0 & 255, m_to = (m_pk0 >> 8) & 255, m_cd = (m_pk0 >> 16) & 255, m_cz = m_pk0 >> 24;
+    const int m_fa = m_pk1 & 255, m_rs = (m_pk1 >> 8) & 255, m_ld = (m_pk1 >> 16) & 255, m_valid = m_pk1 >> 24;
+    // ---- one reduction per CTA
+    if (c.collect_metrics) {
+        const int lane = tid & 31, warp = tid >> 5;
+        const double srew = warp_sum(m_rew), sret = warp_sum(m_ret);
+        const int v[9] = {m_valid, m_done, m_len, m_to, m_cd, m_cz, m_fa, m_rs, m_ld};
+        int r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) r[k] = __reduce_add_sync(0xffffffffu, v[k]);
+        if (lane == 0) {
+            s_m[warp][0] = srew; s_m[warp][1] = sret;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s_m[warp][2 + k] = r[k];
+        }
+        __syncthreads();
+        if (tid < 11) {
+            double acc = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < kTile / 32; ++wv) acc += s_m[wv][tid];
+            const int idx = tid < 2 ? tid : (tid == 10 ? 2 : tid + 6);
+            if (acc != 0.0) atomicAdd(pl.metrics + (blockIdx.x % kMetricSlots) * kMetricStride + idx, acc);
+        }
+    }
+    if (tid == 0) {
+        bulk_wait_read_all();
+        // the step counter is advanced by the last CTA of the LAST launch of a step: this kernel when N is a whole number of
+        // tiles, otherwise the one-block tail launch of quad_step_kernel that follows it on the stream
+        __threadfence();
+        const unsigned long long t = atomicAdd(pl.ctrl + 3, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1ull) {      // last CTA of this launch: re-arm the tile scheduler
+            pl.ctrl[3] = 0ull;
+            pl.ctrl[2] = 0ull;
+            if (do_ticket) pl.ctrl[0] = step + 1ull;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ mode B
@@ -411,7 +583,7 @@ __global__ void apply_resets_kernel(const DevCfg c, const Planes pl, const int64
 
 __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { pl.ctrl[0] = 0ull; pl.ctrl[1] = 0ull; }
+    if (i == 0) { pl.ctrl[0] = 0ull; pl.ctrl[1] = 0ull; pl.ctrl[2] = 0ull; pl.ctrl[3] = 0ull; }
     if (i < kMetricSlots * kMetricStride) pl.metrics[i] = 0.0;
     if (i >= c.num_envs) return;
     Env e;
@@ -569,20 +741,21 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     derive_dev_cfg(*cfg, e->dev);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets >= 3 tiles (measured crossover ~300k envs) (override: OZL_TMA_MIN_TILES, 0 = never)
+        const char* ev = getenv("OZL_TMA_MIN_TILES");
+        e->tma_min_tiles = ev ? atoll(ev) : 3ll * prop.multiProcessorCount * OZL_TMA_MINB;
+    }
     const size_t n = (size_t)cfg->num_envs;
-    const size_t plane4 = align_up(n * sizeof(float4), 256), plane2 = align_up(n * sizeof(float2), 256);
+    const size_t tiles = (n + kTile - 1) / kTile;
+    const size_t plane4 = align_up(tiles * kTile * sizeof(float4), 256), plane2 = align_up(tiles * kTile * sizeof(float2), 256);
+    const size_t state = OZL_TILED ? align_up(tiles * (size_t)kTileBytes, 256) : 7 * plane4 + plane2;
     const size_t ctrl = 256, metrics = align_up(sizeof(double) * kMetricSlots * kMetricStride, 256);
-    e->arena_bytes = 7 * plane4 + plane2 + ctrl + metrics;
+    e->arena_bytes = state + ctrl + metrics;
     if (check_cuda(cudaMalloc(&e->arena, e->arena_bytes), "cudaMalloc(state arena)")) { delete e; return 1; }
+    if (check_cuda(cudaMemset(e->arena, 0, e->arena_bytes), "cudaMemset(state arena)")) { cudaFree(e->arena); delete e; return 1; }
     char* p = (char*)e->arena;
-    e->pl.d0 = (float4*)p; p += plane4;
-    e->pl.d1 = (float4*)p; p += plane4;
-    e->pl.d2 = (float4*)p; p += plane4;
-    e->pl.d3 = (float4*)p; p += plane4;
-    e->pl.s0 = (float4*)p; p += plane4;
-    e->pl.s1 = (float4*)p; p += plane4;
-    e->pl.s2 = (float4*)p; p += plane4;
-    e->pl.d4 = (float2*)p; p += plane2;
+    e->pl.base = p; e->pl.plane4 = (int64_t)plane4; e->pl.plane2 = (int64_t)plane2;
+    p += state;
     e->pl.ctrl = (unsigned long long*)p; p += ctrl;
     e->pl.metrics = (double*)p;
     *out = e;
@@ -622,9 +795,26 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
     cudaStream_t st = (cudaStream_t)stream;
     if (!actions || !obs || !rew || !reset || !progress) return set_error("%s: NULL buffer", who);
     if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("%s: actions/obs must be 16-byte aligned", who);
-    quad_step_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
+    const int64_t n = env->cfg.num_envs;
+    const int64_t full_tiles = n / kTile, tail = n % kTile;
+    const int64_t resident = (int64_t)env->sm_count * OZL_TMA_MINB;
+    const bool plain = (target_in == nullptr) && act_mode == ACT_ROTORS && done_u8 == nullptr && obs_bulk;
+    if (plain && env->tma_min_tiles > 0 && full_tiles >= env->tma_min_tiles &&
+        !(((uintptr_t)progress | (uintptr_t)reset) & 15)) {
+        // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
+        unsigned grid = (unsigned)(full_tiles < resident ? full_tiles : resident);
+        while ((full_tiles + grid - 1) / grid > 120) grid *= 2;      // 8-bit packed metric counters: keep tiles per CTA well below 255
+        quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
+                                                      ep_ret, full_tiles, tail == 0 ? 1 : 0);
+        if (check_cuda(cudaGetLastError(), "quad_step_tma_kernel")) return 1;
+        if (tail)
+            quad_step_kernel<kStepBlock><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress,
+                                                                  timeout, ep_ret, nullptr, ACT_ROTORS, nullptr, 1, full_tiles * kTile);
+        return check_cuda(cudaGetLastError(), "quad_step_kernel(tail)");
+    }
+    quad_step_kernel<kStepBlock><<<blocks_for(n, kStepBlock), kStepBlock, 0, st>>>(
         env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8,
-        obs_bulk);
+        obs_bulk, 0);
     return check_cuda(cudaGetLastError(), "quad_step_kernel");
 }
 
