@@ -300,10 +300,11 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 2, 1ull);
     }
 
-    // metric accumulators over all tiles of this CTA (small counts packed 8 bits each: a CTA handles far fewer than 255 tiles)
+    // metric accumulators over all tiles of this CTA (per-thread counts packed 16 bits each; the host keeps the average number of
+    // tiles per CTA below 8192, and the dynamic scheduler spreads them evenly)
     double m_rew = 0.0, m_ret = 0.0;
     int m_len = 0;
-    uint32_t m_pk0 = 0, m_pk1 = 0;      // pk0: done | timeout | crash_dist | crash_z ; pk1: fault_active | resets | landed | tiles
+    uint32_t m_pk0 = 0, m_pk1 = 0, m_pk2 = 0, m_pk3 = 0;   // done|timeout, crash_dist|crash_z, fault_active|resets, landed|tiles
     uint32_t phase = 0;
     while (tile < full_tiles) {
         mbar_wait(&s_bar, phase);
@@ -353,12 +354,14 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         // metrics
         m_rew += (double)o.rew;
         if (o.reset) { m_ret += (double)o.ep_ret_done; m_len += (int)o.prog; }
-        m_pk0 += (uint32_t)o.reset | ((uint32_t)o.timeout << 8) | ((uint32_t)o.crash_dist << 16) | ((uint32_t)o.crash_z << 24);
-        m_pk1 += (uint32_t)o.fault_active | ((uint32_t)o.did_reset << 8) | ((uint32_t)o.landed_episode << 16) | (1u << 24);
+        m_pk0 += (uint32_t)o.reset | ((uint32_t)o.timeout << 16);
+        m_pk1 += (uint32_t)o.crash_dist | ((uint32_t)o.crash_z << 16);
+        m_pk2 += (uint32_t)o.fault_active | ((uint32_t)o.did_reset << 16);
+        m_pk3 += (uint32_t)o.landed_episode | (1u << 16);
         tile = next;
     }
-    const int m_done = m_pk0 & 255, m_to = (m_pk0 >> 8) & 255, m_cd = (m_pk0 >> 16) & 255, m_cz = m_pk0 >> 24;
-    const int m_fa = m_pk1 & 255, m_rs = (m_pk1 >> 8) & 255, m_ld = (m_pk1 >> 16) & 255, m_valid = m_pk1 >> 24;
+    const int m_done = m_pk0 & 0xFFFF, m_to = m_pk0 >> 16, m_cd = m_pk1 & 0xFFFF, m_cz = m_pk1 >> 16;
+    const int m_fa = m_pk2 & 0xFFFF, m_rs = m_pk2 >> 16, m_ld = m_pk3 & 0xFFFF, m_valid = m_pk3 >> 16;
     // ---- one reduction per CTA
     if (c.collect_metrics) {
         const int lane = tid & 31, warp = tid >> 5;
@@ -803,7 +806,7 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         !(((uintptr_t)progress | (uintptr_t)reset) & 15)) {
         // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
         unsigned grid = (unsigned)(full_tiles < resident ? full_tiles : resident);
-        while ((full_tiles + grid - 1) / grid > 120) grid *= 2;      // 8-bit packed metric counters: keep tiles per CTA well below 255
+        while ((full_tiles + grid - 1) / grid > 8192) grid *= 2;     // 16-bit packed metric counters: keep tiles per CTA far below 65535
         quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
                                                       ep_ret, full_tiles, tail == 0 ? 1 : 0);
         if (check_cuda(cudaGetLastError(), "quad_step_tma_kernel")) return 1;
@@ -827,8 +830,9 @@ extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs
                              int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
     if (!done_host) return set_error("ozl_step_host: done_host is NULL");
     // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store
+    static const int host_bulk = getenv("OZL_HOST_BULK") ? atoi(getenv("OZL_HOST_BULK")) : 0;
     return launch_step(env, actions_host, nullptr, ACT_ROTORS, obs_host, rew_host, reset, progress, timeout, ep_ret, stream,
-                       "ozl_step_host", done_host, 0);
+                       "ozl_step_host", done_host, host_bulk);
 }
 
 extern "C" int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,
