@@ -152,6 +152,31 @@ class X500Task(VecTask):
         the reference's takes effect: pre_physics_step, ouzelum.py:226-229); here the request is recorded."""
         self.reset_buf[env_ids] = 1
 
+    # ---- checkpoint / resume of the ENV state (the reference never saves it; SURVEY section 5) ----------------------------
+    def state_dict(self):
+        """Everything needed to continue bit-identically: private state, per-env parameters, RNG time axis, surface buffers."""
+        st = self.sim.get_state()
+        params, fault = self.sim.get_params()
+        torch.cuda.current_stream().synchronize()
+        return {"root": st["root"].cpu(), "thrust": st["thrust"].cpu(), "target": st["target"].cpu(), "ep_ret": st["ep_ret"].cpu(),
+                "params": params.cpu(), "fault": fault.cpu(), "step_count": self.sim.step_count,
+                "reset_buf": self.reset_buf.cpu(), "progress_buf": self.progress_buf.cpu(), "obs_buf": self.obs_buf.cpu(),
+                "rew_buf": self.rew_buf.cpu(), "seed": int(self.native_cfg.seed), "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd):
+        if sd["num_envs"] != self.num_envs:
+            raise ValueError(f"checkpoint has {sd['num_envs']} envs, this env has {self.num_envs}")
+        if sd["seed"] != int(self.native_cfg.seed):
+            raise ValueError("checkpoint was taken with a different RNG seed")
+        self.sim.set_state(root=sd["root"], thrust=sd["thrust"], target=sd["target"], ep_ret=sd["ep_ret"])
+        self.sim.set_params(sd["params"], sd["fault"])
+        self.sim.step_count = sd["step_count"]
+        self.reset_buf.copy_(sd["reset_buf"])
+        self.progress_buf.copy_(sd["progress_buf"])
+        self.obs_buf.copy_(sd["obs_buf"])
+        self.rew_buf.copy_(sd["rew_buf"])
+        self._graph = None
+
     def metrics(self, clear=False):
         """Episode / reward metrics vector accumulated in-kernel (see include/ouzelum_b200.h)."""
         return self.sim.metrics(clear=clear)

@@ -15,6 +15,9 @@ import torch
 
 from .spaces import Box
 
+import os as _os
+_NVTX = _os.environ.get("OUZELUM_B200_NVTX", "0") == "1"
+
 
 class Env:
     def __init__(self, config: Dict[str, Any], rl_device: str, sim_device: str, graphics_device_id: int, headless: bool):
@@ -118,7 +121,12 @@ class VecTask(Env):
         observation clamp all happen inside the one kernel `_fused_step` launches."""
         if actions.dtype != torch.float32 or not actions.is_contiguous() or str(actions.device) != self.device:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
-        self._fused_step(actions)
+        if _NVTX:                                   # OUZELUM_B200_NVTX=1: one NVTX range per env step (nsys / ncu --nvtx)
+            torch.cuda.nvtx.range_push(f"{type(self).__name__}.step")
+            self._fused_step(actions)
+            torch.cuda.nvtx.range_pop()
+        else:
+            self._fused_step(actions)
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
         if self.num_states > 0:

@@ -324,3 +324,64 @@ def test_landed_writes_reference_log_formats(tmp_path):
     assert all(len(r) == 6 for r in rows) and abs(float(rows[0][5]) - 0.377) < 1e-6          # target z == 0.377 (landed.py:78)
     assert abs(float(rows[0][0])) <= 1.51 and 0.7 <= float(rows[0][2]) <= 2.6               # spawn ranges (landed.py:232-235)
     assert int((tmp_path / "metrics" / "flicker_0.01.txt").read_text()) == env.landings
+
+
+def test_env_checkpoint_resume_is_bit_identical():
+    """state_dict / load_state_dict: a restored env continues exactly like the original (state, parameters, RNG time axis)."""
+    import ouzelum_b200
+    n = 1000
+    mk = lambda: ouzelum_b200.make(seed=13, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                   cfg=ouzelum_b200.task_config("Ouzelum", n, seed=13, rotorFault={"enable": True},
+                                                                domainRandomization={"enable": True}, maxEpisodeLength=50))
+    e1 = mk()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    acts = [torch.rand(n, 4, device=DEV, generator=g) * 2 - 1 for _ in range(80)]
+    for t in range(40):
+        e1.step(acts[t])
+    sd = e1.state_dict()
+    e2 = mk()
+    e2.load_state_dict(sd)
+    for t in range(40, 80):
+        o1, r1, d1, _ = e1.step(acts[t])
+        o2, r2, d2, _ = e2.step(acts[t])
+        assert torch.equal(o1["obs"], o2["obs"]) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+    assert torch.equal(e1.root_states, e2.root_states)
+    p1, f1 = e1.sim.get_params()
+    p2, f2 = e2.sim.get_params()
+    assert torch.equal(p1, p2) and torch.equal(f1, f2)
+    with pytest.raises(ValueError):
+        ouzelum_b200.make(seed=13, task="Ouzelum", num_envs=n + 1, sim_device=DEV, rl_device=DEV, headless=True).load_state_dict(sd)
+
+
+def test_determinism_and_seed_sensitivity():
+    import ouzelum_b200
+    n = 512
+    runs = []
+    for seed in (5, 5, 6):
+        env = ouzelum_b200.make(seed=seed, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+        for t in range(30):
+            o, r, d, _ = env.step(torch.full((n, 4), 0.1, device=DEV))
+        runs.append(o["obs"].clone())
+    assert torch.equal(runs[0], runs[1]) and not torch.equal(runs[0], runs[2])
+
+
+def test_c_abi_error_paths_are_reported():
+    import ctypes as C
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+    lib = _lib.lib
+    sim = QuadSim(_lib.default_cfg(64), DEV)
+    z = torch.zeros(64, 13, device=DEV)
+    assert lib.ozl_step(sim._h, None, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, None, None) != 0
+    assert "NULL" in _lib.last_error()
+    assert lib.ozl_step(sim._h, z.data_ptr() + 4, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, None, None) != 0
+    assert "aligned" in _lib.last_error()
+    assert lib.ozl_rollout(sim._h, 0, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None) != 0
+    bad = _lib.default_cfg(64)
+    bad.abi_version = 99
+    h = C.c_void_p()
+    assert lib.ozl_create(C.byref(bad), 0, C.byref(h)) != 0 and "abi_version" in _lib.last_error()
+    assert lib.ozl_create(C.byref(_lib.default_cfg(64)), 99, C.byref(h)) != 0 and "not available" in _lib.last_error()
+    assert lib.ozl_lee_control(7, 8, z.data_ptr(), z.data_ptr(), (C.c_float * 16)(), z.data_ptr(), z.data_ptr(), None) != 0
+    assert "Invalid controller name" in _lib.last_error()
+    assert lib.ozl_pomdp_observation(8, 13, 0, 0.1, 0, 0, 0, 0, z.data_ptr(), z.data_ptr(), None) != 0
