@@ -167,14 +167,8 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         }
         const float act[4] = {a4.x, a4.y, a4.z, a4.w};
         const uint32_t genv = c.env_id_base + (uint32_t)i;
-#ifdef OZL_EXPERIMENT_NO_COMPUTE   // memory-system ceiling experiment only (never shipped)
-        for (int j = 0; j < 3; ++j) { e.p[j] += act[j] + e.tgt[j] + e.inv_m; e.v[j] += e.ixx + e.arm; o.obs[j] = e.p[j]; o.obs[3 + j] = e.v[j]; o.obs[6 + j] = e.w[j]; o.obs[9 + j] = e.q[j]; }
-        o.obs[12] = e.T[3] + e.eff + e.mass + __uint_as_float(e.fault);
-        o.rew = e.ep_ret; o.prog = prog + 1; o.reset = rst;
-#else
         env_step(e, act, prog, rst, genv, step, c, o, act_mode, target_in ? tnew : nullptr);
         obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
-#endif
 
         store_dynamic(pl, i, e);
         if (o.static_dirty || target_in) store_static(pl, i, e);
@@ -806,6 +800,7 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         !(((uintptr_t)progress | (uintptr_t)reset) & 15)) {
         // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
         unsigned grid = (unsigned)(full_tiles < resident ? full_tiles : resident);
+        { static const char* eg = getenv("OZL_TMA_GRID"); if (eg && atoi(eg) > 0 && (int64_t)atoi(eg) <= full_tiles) grid = (unsigned)atoi(eg); }   // tuning aid
         while ((full_tiles + grid - 1) / grid > 8192) grid *= 2;     // 16-bit packed metric counters: keep tiles per CTA far below 65535
         quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
                                                       ep_ret, full_tiles, tail == 0 ? 1 : 0);
