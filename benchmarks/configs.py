@@ -69,10 +69,16 @@ def config3():
     env = ouzelum_b200.make(seed=0, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
     a = torch.zeros(n, 4, device=DEV)
     dt = timed(lambda: env.step(a), steps, 40)
+    cfg2 = ouzelum_b200.task_config("EKFLeeLanded", n, seed=0, POMDP="random_noise", pomdp_prob=0.15, ConvergenceTime=20,
+                                    domainRandomization={"enable": True}, rotorFault={"enable": True}, useCudaGraph=True,
+                                    perEnvSensorTriggers=True)
+    env2 = ouzelum_b200.make(seed=0, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg2)
+    dt2 = timed(lambda: env2.step(a), steps, 40)
     alg = 1372
     return {"config": 3, "workload": "x500 + DR + sensor noise sigma 0.15 + EKF (f64) + PV filter (full 9x9) + Lee controller, 65536 envs",
             "env_steps_per_sec": n * steps / dt, "us_per_step": dt / steps * 1e6, "alg_bytes_per_env_step": alg,
             "achieved_GBps_alg": alg * n * steps / dt / 1e9, "launches_per_step": 3,
+            "per_env_sensor_triggers_env_steps_per_sec": n * steps / dt2,
             "landings": env.landings, "episodes": env.episodes}
 
 

@@ -80,7 +80,7 @@ class EKFLeeLanded(_VehicleTargetTask):
         a.dt, a.mg, a.hover_force = self.dt, self.mg, float(self._hover[0, 0].item())
         a.convergence_steps = int(self.ConvergenceTime)
         a.pomdp_mode, a.pomdp_prob = self._pomdp_mode, self._pomdp_prob
-        pp, ph, vp, vh = (1, 0, 1, 0) if self.per_env_triggers else self._trigger
+        pp, ph, vp, vh = self._trigger
         a.pos_period, a.pos_phase = (pp if self.attach_pos_sensor else 0), ph
         a.vel_period, a.vel_phase = (vp if self.attach_vel_sensor else 0), vh
         a.per_env_triggers = 1 if self.per_env_triggers else 0
@@ -138,13 +138,13 @@ class EKFLeeLanded(_VehicleTargetTask):
         self.ekf.update(gyr, ang, ang_xyzw=True, q_f32_out=self._q32)                  # :378-391
         self.pvfilters.reset_states(self._root, self.reset_buf)                        # :353-358
         acc, pos, vel = sens[:, 0:3].contiguous(), sens[:, 10:13].contiguous(), sens[:, 13:16].contiguous()
-        trig = (1, 0, 1, 0) if self.per_env_triggers else self._trigger
+        trig = self._trigger
         trig = (trig[0] if self.attach_pos_sensor else 0, trig[1], trig[2] if self.attach_vel_sensor else 0, trig[3])
         self.pvfilters.step(accels=acc, orientation=quat_true if warm else self._q32, dt=self.dt, flip_Qw=bool(warm),
                             gps_data=pos, gps_var=[0.0000001] * 3,                     # :408,430
                             vel_data=vel, vel_var=None,     # the reference's velocity fix runs with R = 0 (PVFilter.py:76-79)
                             trigger=trig,
-                            iter_base=0 if self.per_env_triggers else self.sim_step_count * n)   # :417-444
+                            iter_base=self.sim_step_count * n)   # :417-444
         check(lib.ozl_waypoint_command(n, self._root.data_ptr(), self.pvfilters._x.data_ptr(), self._target.data_ptr(),
                                        self.target_waypoints.data_ptr(), 1 if warm else 0, self._est.data_ptr(),
                                        self._cmd.data_ptr(), s))                        # :458-503

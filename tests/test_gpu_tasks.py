@@ -385,3 +385,40 @@ def test_c_abi_error_paths_are_reported():
     assert lib.ozl_lee_control(7, 8, z.data_ptr(), z.data_ptr(), (C.c_float * 16)(), z.data_ptr(), z.data_ptr(), None) != 0
     assert "Invalid controller name" in _lib.last_error()
     assert lib.ozl_pomdp_observation(8, 13, 0, 0.1, 0, 0, 0, 0, z.data_ptr(), z.data_ptr(), None) != 0
+
+
+def test_ekf_lee_per_env_trigger_mode_vs_oracle():
+    """`perEnvSensorTriggers`: every env counts its own steps (position fix every 7th, velocity fix every 3rd step) instead of
+    the reference's counters shared by all envs (ekf_lee_landed.py:425-440) -- SURVEY appendix A asks for both modes."""
+    import ouzelum_b200
+    from oracle.ekf_lee_landed import EKFLeeGlue
+    n, conv = 64, 4
+    cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=9, ConvergenceTime=conv, POMDP="none", maxEpisodeLength=40,
+                                   perEnvSensorTriggers=True)
+    env = ouzelum_b200.make(seed=9, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
+    ora = EKFLeeGlue(n, convergence=conv, seed=9, per_env_triggers=True)
+    a = torch.zeros(n, 4, device=DEV)
+    for t in range(30):
+        reset_before = env.reset_buf.bool().cpu().numpy().copy()
+        ora.Q, ora.ekf.P = env.ekf.Q_state.cpu().numpy().copy(), env.ekf.P.cpu().numpy().copy()
+        ora.pv.state, ora.pv.cov = env.pvfilters.get_states().cpu().numpy().copy(), env.pvfilters.get_covariances().cpu().numpy().copy()
+        ora.prev_v, ora.waypoints = env.prev_root_linvels.cpu().numpy().copy(), env.target_waypoints.cpu().numpy().copy()
+        root_before = env.sim.get_state()["root"].cpu().numpy()
+        cov_before = env.pvfilters.get_covariances().cpu().numpy().copy()
+        env.step(a)
+        # the fused kernel re-spawns reset envs in registers: rebuild the post-reset truth it saw
+        from oracle import philox as px
+        root = root_before.copy()
+        if reset_before.any():
+            r0, r1, r2, _ = px.draw(9, np.arange(n), t, px.P_SPAWN)
+            sp = np.stack([np.float32(3.0) * px.u01(r0) + np.float32(-1.5), np.float32(3.0) * px.u01(r1) + np.float32(-1.5),
+                           np.float32(1.0) + (np.float32(1.7) * px.u01(r2) + np.float32(-0.2))], 1)
+            root[reset_before] = 0
+            root[reset_before, 0:3] = sp[reset_before]
+            root[reset_before, 6] = 1
+        ora.pre_physics(root, env._target.cpu().numpy(), reset_before)
+        sx = np.abs(ora.pv.state).max() + 1.0
+        np.testing.assert_allclose(env.pvfilters.get_states().cpu().numpy(), ora.pv.state, rtol=2e-3, atol=2e-4 * sx, err_msg=f"t={t}")
+        scov = np.abs(ora.pv.cov).max() + 1.0
+        tight = np.isclose(env.pvfilters.get_covariances().cpu().numpy(), ora.pv.cov, rtol=2e-3, atol=1e-5 * scov)
+        assert tight.mean() > 0.995, f"t={t}: covariance disagrees with the per-env-trigger oracle"
