@@ -114,9 +114,12 @@ def _cpu_oracle(n_envs, seed, flavour):
     from oracle.quad_step import QuadStepOracle, default_cfg
     cfg = default_cfg(n_envs, seed=seed, **{k: v for k, v in task_cfg_kwargs().items() if k != "collect_metrics"})
     if flavour == "c":
-        from oracle.c_oracle import COracle, make_cfg
-        ora = COracle(make_cfg(QuadStepOracle(cfg).cfg))          # QuadStepOracle rounds the float fields exactly like the struct
-        return ora, (lambda a: ora.step(a.numpy()))
+        try:
+            from oracle.c_oracle import COracle, make_cfg
+            ora = COracle(make_cfg(QuadStepOracle(cfg).cfg))      # QuadStepOracle rounds the float fields exactly like the struct
+            return ora, (lambda a: ora.step(a.numpy()))
+        except Exception as e:                                    # no C compiler on the box: fall back to the torch-eager port
+            sys.stderr.write(f"[bench] C oracle unavailable ({e!r}); using the torch-eager port\n")
     torch.set_num_threads(os.cpu_count() or 1)
     ora = QuadStepOracle(cfg)
     return ora, ora.step
