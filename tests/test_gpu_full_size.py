@@ -1,0 +1,84 @@
+"""Parity at BASELINE.json's full sizes (config 4: 1 Mi envs).  The C oracle is fast enough to check EVERY env bit for bit
+at this size; on top of that come size-independent properties: the TMA-pipelined kernel and the generic kernel are the same
+function, sharding is pure slicing, and the metrics vector conserves env-steps / resets / episodes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bufs(n):
+    return dict(obs=torch.zeros(n, 13, device=DEV), rew=torch.zeros(n, device=DEV),
+                reset=torch.ones(n, dtype=torch.int64, device=DEV), progress=torch.zeros(n, dtype=torch.int64, device=DEV),
+                timeout=torch.zeros(n, dtype=torch.uint8, device=DEV), ep_ret=torch.zeros(n, device=DEV))
+
+
+def _mk(n, tma, **kw):
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+    old = os.environ.get("OZL_TMA_MIN_TILES")
+    os.environ["OZL_TMA_MIN_TILES"] = "1" if tma else "0"       # read once per handle at ozl_create
+    try:
+        return QuadSim(_lib.default_cfg(n, **kw), DEV)
+    finally:
+        if old is None:
+            os.environ.pop("OZL_TMA_MIN_TILES", None)
+        else:
+            os.environ["OZL_TMA_MIN_TILES"] = old
+
+
+def test_one_million_envs_tma_vs_generic_vs_c_oracle():
+    from ouzelum_b200 import _lib
+    from oracle.c_oracle import COracle
+    n, steps = (1 << 20) + 77, 24                               # ragged: 8192 whole tiles + a 77-env tail
+    kw = dict(seed=2024, fault_mode=1, dr_enable=1, max_episode_length=20)
+    a_sim, b_sim = _mk(n, True, **kw), _mk(n, False, **kw)
+    co = COracle(_lib.default_cfg(n, **kw))
+    a, b = _bufs(n), _bufs(n)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for t in range(steps):
+        act = torch.rand(n, 4, device=DEV, generator=g) * 2 - 1
+        a_sim.step(act, a["obs"], a["rew"], a["reset"], a["progress"], a["timeout"], a["ep_ret"])
+        b_sim.step(act, b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+        co.step(act.cpu().numpy())
+        if t in (0, 1, 11, steps - 1):
+            for k in ("obs", "rew", "reset", "progress", "timeout", "ep_ret"):
+                assert torch.equal(a[k], b[k]), f"TMA vs generic differ in {k} at step {t}"
+            assert np.array_equal(a["obs"].cpu().numpy(), co.obs_buf), t
+            assert np.array_equal(a["reset"].cpu().numpy(), co.reset_buf), t
+            assert np.array_equal(a["progress"].cpu().numpy(), co.progress_buf), t
+            assert np.array_equal(a["rew"].cpu().numpy(), co.rew_buf), t
+    sa, sb = a_sim.get_state(), b_sim.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert np.array_equal(sa["root"].cpu().numpy(), co.root)
+    ma, mb = a_sim.metrics().cpu().numpy(), b_sim.metrics().cpu().numpy()
+    np.testing.assert_array_equal(ma[8:16], mb[8:16])
+    np.testing.assert_allclose(ma[0:2], mb[0:2], rtol=1e-9)
+    # conservation laws of the metrics vector
+    assert ma[8] == n * steps                                   # env-steps
+    assert ma[15] == n + ma[9] - int(a["reset"].sum())          # resets applied = initial resets + finished episodes not yet re-spawned
+    assert ma[11] > 0 and ma[12] + ma[13] > 0                   # time-outs and crashes both occurred
+    assert a_sim.step_count == b_sim.step_count == steps
+
+
+def test_sharding_is_pure_slicing_at_scale():
+    n, parts, steps = 1 << 19, 4, 12
+    kw = dict(seed=11, fault_mode=1, dr_enable=1)
+    whole, wb = _mk(n, True, **kw), _bufs(n)
+    per = n // parts
+    shards = [(_mk(per, False, env_id_base=j * per, **kw), _bufs(per)) for j in range(parts)]
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for t in range(steps):
+        act = torch.rand(n, 4, device=DEV, generator=g) * 2 - 1
+        whole.step(act, wb["obs"], wb["rew"], wb["reset"], wb["progress"], wb["timeout"], wb["ep_ret"])
+        for j, (s, b) in enumerate(shards):
+            s.step(act[j * per:(j + 1) * per].contiguous(), b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+    for k in ("obs", "rew", "reset", "progress"):
+        assert torch.equal(wb[k], torch.cat([b[k] for _, b in shards])), k
+    tot = sum(s.metrics().cpu().numpy()[8:16] for s, _ in shards)
+    np.testing.assert_array_equal(whole.metrics().cpu().numpy()[8:16], tot)     # what the NCCL all-reduce would produce
