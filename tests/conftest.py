@@ -1,3 +1,4 @@
+import importlib.util
 import os
 import sys
 
@@ -10,6 +11,22 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _load_build_script():
+    spec = importlib.util.spec_from_file_location("_ozl_build", os.path.join(ROOT, "ouzelum_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session", autouse=True)
+def native_library():
+    """The product refuses to import without libouzelum_b200.so (no fallback).  The test session therefore makes sure the
+    in-tree library exists and is up to date (a no-op when `__graft_entry__.build()` already ran); nvcc cross-compiles
+    sm_100a without a GPU."""
+    _load_build_script().build()
+    yield
 
 
 @pytest.fixture(scope="session")
