@@ -121,12 +121,16 @@ def config5():
     dt_fp32 = timed(f, iters, 3)
     torch.backends.cuda.matmul.allow_tf32 = True          # the policy GEMMs on tensor cores (TF32); the env kernels are unaffected
     dt = timed(f, iters, 3)
+    from ouzelum_b200.rollout import GraphedRollout
+    gro = GraphedRollout(env, actor, store, pomdp)
+    dt_graph = timed(gro.run, iters, 3)
     # env-kernel share: the same number of env steps without the policy
     a = torch.zeros(n, 4, device=DEV)
     dte = timed(lambda: env.step(a), iters * T, 10)
     return {"config": 5, "workload": "RPO-LSTM rollout collection: Landing task + flicker 0.1 + MLP(13-512-256)+LSTM(256-128) policy, 32768 envs, 16-step rollouts",
             "env_steps_per_sec": n * T * iters / dt, "us_per_env_step_call": dt / (iters * T) * 1e6,
-            "env_steps_per_sec_fp32_simt_policy": n * T * iters / dt_fp32, "policy_matmul": "TF32 tensor cores (torch.backends.cuda.matmul.allow_tf32)",
+            "env_steps_per_sec_fp32_simt_policy": n * T * iters / dt_fp32,
+            "env_steps_per_sec_cuda_graph": n * T * iters / dt_graph, "us_per_env_step_call_cuda_graph": dt_graph / (iters * T) * 1e6, "policy_matmul": "TF32 tensor cores (torch.backends.cuda.matmul.allow_tf32)",
             "env_only_us_per_step": dte / (iters * T) * 1e6, "env_share_of_wall": dte / dt}
 
 

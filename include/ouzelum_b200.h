@@ -265,6 +265,10 @@ int ozl_step_counter_ptr(ozl_env* env, const uint64_t** out);
  * Draws are counter-based: (seed, global env id, step, stream_id) -- stream_id separates several uses in one step. */
 int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step,
                           int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream);
+/* Same, with the call index read from a DEVICE counter (ozl_step_counter_ptr) -- no host-changing argument, so a whole
+ * policy -> step -> sensor-fault iteration can sit in one CUDA graph. */
+int ozl_pomdp_observation_dev(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, const uint64_t* step_ptr,
+                              int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream);
 
 /* RecordEpisodeStatisticsTorch.step (isaacgymenvs/RPO-LSTM/utils.py:20-35) in one launch:
  * ep_ret += rew; ep_len += 1; ret_out = ep_ret; len_out = ep_len; ep_ret *= 1-done; ep_len *= 1-done. */

@@ -142,6 +142,8 @@ _SIGS = {
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_husky_step": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_quadcopter_step": (C.c_int, [C.POINTER(OzlQuadcopterArgs), _P]),
+    "ozl_pomdp_observation_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, C.c_int64, C.c_int32,
+                                            _P, _P, _P]),
     "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -157,9 +157,10 @@ __global__ void ekf_set_q_kernel(int64_t n, double* q, const float* quat_xyzw, c
 // uses env word GLOBAL_ENV.  `stream_id` separates several uses within one step (gyro / accel / pos / vel ...).
 __global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float noise_lo, float noise_range, uint64_t seed,
                              uint64_t step, uint32_t env_id_base, uint32_t stream_id, const float* __restrict__ in,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, const unsigned long long* __restrict__ step_ptr) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (step_ptr) step = *reinterpret_cast<const volatile unsigned long long*>(step_ptr);   // follow a device step counter
     bool blackout = false;
     if (mode == 1 || mode == 3) {
         const uint4 r = draw(seed, GLOBAL_ENV, step, P_FLICKER + (stream_id << 8));
@@ -377,8 +378,23 @@ extern "C" int ozl_waypoint_command(int64_t n, const float* root13, const float*
     return check_cuda(cudaGetLastError(), "waypoint_kernel");
 }
 
+static int pomdp_launch(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step, const uint64_t* step_ptr,
+                        int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream);
+
 extern "C" int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step,
                                      int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream) {
+    return pomdp_launch(n, d, mode, pomdp_prob, seed, step, nullptr, env_id_base, stream_id, in, out, stream);
+}
+
+extern "C" int ozl_pomdp_observation_dev(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed,
+                                         const uint64_t* step_ptr, int64_t env_id_base, int32_t stream_id, const float* in,
+                                         float* out, void* stream) {
+    if (!step_ptr) return set_error("ozl_pomdp_observation_dev: step_ptr is NULL");
+    return pomdp_launch(n, d, mode, pomdp_prob, seed, 0, step_ptr, env_id_base, stream_id, in, out, stream);
+}
+
+static int pomdp_launch(int64_t n, int32_t d, int32_t mode, float pomdp_prob, uint64_t seed, uint64_t step, const uint64_t* step_ptr,
+                        int64_t env_id_base, int32_t stream_id, const float* in, float* out, void* stream) {
     OZL_N_CHECK("ozl_pomdp_observation");
     if (mode < 1 || mode > 3)
         return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");   // POMDP.py:19-20
@@ -386,7 +402,7 @@ extern "C" int ozl_pomdp_observation(int64_t n, int32_t d, int32_t mode, float p
     const float flick = (mode == 3) ? 0.1f : pomdp_prob;                                   // POMDP.py:16-18
     const float lo = (float)(1.0 - (double)pomdp_prob), hi = (float)(1.0 + (double)pomdp_prob);
     pomdp_kernel<<<nblk(n, 256), 256, 0, st>>>(n, d, mode, flick, lo, hi - lo, seed, step, (uint32_t)env_id_base,
-                                               (uint32_t)stream_id, in, out);
+                                               (uint32_t)stream_id, in, out, (const unsigned long long*)step_ptr);
     return check_cuda(cudaGetLastError(), "pomdp_kernel");
 }
 

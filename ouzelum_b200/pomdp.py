@@ -25,6 +25,15 @@ class POMDPWrapper:
         self.mode = _MODES[pomdp]
         self.seed, self.env_id_base, self.stream_id = int(seed), int(env_id_base), int(stream_id)
         self.calls = 0
+        self._step_ptr = None
+
+    def follow_step_counter(self, env):
+        """Take the call index from `env`'s device step counter instead of the host-side call count: `observation` then has
+        no host-changing argument and can be captured in a CUDA graph together with the env step."""
+        import ctypes as C
+        p = C.c_void_p()
+        check(lib.ozl_step_counter_ptr(env.sim._h, C.byref(p)))
+        self._step_ptr = p.value
 
     def observation(self, obs):
         x = obs.to(torch.float32).contiguous()
@@ -32,8 +41,13 @@ class POMDPWrapper:
             raise RuntimeError("ouzelum_b200.POMDPWrapper needs a CUDA tensor (no CPU fallback)")
         flat = x.reshape(-1, x.shape[-1]) if x.dim() > 1 else x.reshape(1, -1)
         out = torch.empty_like(flat)
-        check(lib.ozl_pomdp_observation(flat.shape[0], flat.shape[1], self.mode, float(self.prob), self.seed, self.calls,
-                                        self.env_id_base, self.stream_id, flat.data_ptr(), out.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream), ValueError)
+        if self._step_ptr is not None:
+            check(lib.ozl_pomdp_observation_dev(flat.shape[0], flat.shape[1], self.mode, float(self.prob), self.seed,
+                                                self._step_ptr, self.env_id_base, self.stream_id, flat.data_ptr(),
+                                                out.data_ptr(), torch.cuda.current_stream().cuda_stream), ValueError)
+        else:
+            check(lib.ozl_pomdp_observation(flat.shape[0], flat.shape[1], self.mode, float(self.prob), self.seed, self.calls,
+                                            self.env_id_base, self.stream_id, flat.data_ptr(), out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), ValueError)
         self.calls += 1
         return out.reshape(x.shape)

@@ -90,3 +90,47 @@ def initial_rollout_state(env, actor):
     obs = env.reset()["obs"]
     return dict(next_obs=obs, pomdp_obs=obs.clone(), next_done=torch.zeros(env.num_envs, device=obs.device),
                 lstm_state=actor.initial_state(env.num_envs, obs.device))
+
+
+class GraphedRollout:
+    """One whole `rollout_steps` collection pass -- T x (policy forward, env step, sensor-fault wrapper) -- captured in ONE CUDA
+    graph and replayed.  Possible because nothing on the env side takes a host-changing argument: the step kernels, the vehicle
+    kernel and the sensor-fault wrapper all follow the env's DEVICE step counter.  SURVEY section 8f rank 1."""
+
+    def __init__(self, env, actor, storage, pomdp=None):
+        self.env, self.actor, self.storage, self.pomdp = env, actor, storage, pomdp
+        if pomdp is not None:
+            pomdp.follow_step_counter(env)
+        self.state = initial_rollout_state(env, actor)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside capture (allocator, cuBLAS workspaces, autotune)
+            for _ in range(2):
+                self._assign(collect_rollout(env, actor, storage, self.state, pomdp))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._assign(collect_rollout(env, actor, storage, self.state, pomdp))
+
+    def _assign(self, new):
+        s = self.state
+        s["next_obs"].copy_(new["next_obs"])
+        s["pomdp_obs"].copy_(new["pomdp_obs"])
+        s["next_done"].copy_(new["next_done"])
+        s["lstm_state"][0].copy_(new["lstm_state"][0])
+        s["lstm_state"][1].copy_(new["lstm_state"][1])
+
+    def run(self):
+        self.graph.replay()
+        return self.storage
+
+
+def save_actor(actor, tag):
+    """Checkpoint file of the reference's trainers: `<tag>_actor` = torch.save(state_dict) (RPO-LSTM/agent.py:136-140)."""
+    torch.save(actor.state_dict(), f"{tag}_actor")
+
+
+def load_actor(actor, tag, map_location=None):
+    actor.load_state_dict(torch.load(f"{tag}_actor", map_location=map_location))     # RPO-LSTM/agent.py:142-147
+    return actor

@@ -39,6 +39,12 @@ class _VehicleTargetTask(X500Task):
         t0[:, 2] = TARGET_Z
         self.sim.set_state(target=t0)
         self._target = self.husky.target
+        # the vehicle kernel follows the env's device step counter: no host-changing launch argument (CUDA-graph capturable)
+        import ctypes as C
+        from .._lib import check, lib
+        ctr = C.c_void_p()
+        check(lib.ozl_step_counter_ptr(self.sim._h, C.byref(ctr)))
+        self.husky.follow_step_counter(ctr.value)
 
     def _launch(self, actions):
         if self.vehicle_moves:

@@ -422,3 +422,31 @@ def test_ekf_lee_per_env_trigger_mode_vs_oracle():
         scov = np.abs(ora.pv.cov).max() + 1.0
         tight = np.isclose(env.pvfilters.get_covariances().cpu().numpy(), ora.pv.cov, rtol=2e-3, atol=1e-5 * scov)
         assert tight.mean() > 0.995, f"t={t}: covariance disagrees with the per-env-trigger oracle"
+
+
+def test_graphed_rollout_collection_runs_and_tracks_step_counter(tmp_path):
+    """Config-5 glue: T x (LSTM policy, env step, sensor-fault wrapper) captured in ONE CUDA graph and replayed."""
+    import ouzelum_b200
+    from ouzelum_b200.pomdp import POMDPWrapper
+    from ouzelum_b200.rollout import GraphedRollout, RecurrentActor, RolloutStorage, load_actor, save_actor
+    n, T = 512, 16
+    env = ouzelum_b200.make(seed=3, task="Landing", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    torch.manual_seed(0)
+    actor = RecurrentActor().to(DEV)
+    store = RolloutStorage(T, n, 13, 4, DEV)
+    gro = GraphedRollout(env, actor, store, POMDPWrapper("random_noise", 0.1))
+    c0 = env.sim.step_count
+    for _ in range(5):
+        gro.run()
+    torch.cuda.synchronize()
+    assert env.sim.step_count == c0 + 5 * T                      # every replay advanced the device step counter by T
+    assert torch.isfinite(store.obs).all() and torch.isfinite(store.rewards).all() and float(store.rewards.abs().sum()) > 0
+    assert float(store.actions.abs().max()) > 0 and store.dones.sum() >= 0
+    m = env.metrics().cpu()
+    assert int(m[8]) == env.sim.step_count * n
+    # sensor-fault wrapper followed the counter: noisy obs differ from clean obs by at most the noise band
+    ratio = (store.pomdps[1:] / store.obs[1:].clamp_min(1e-6))[store.obs[1:] > 1e-3]
+    assert float(ratio.min()) >= 0.9 - 1e-5 and float(ratio.max()) <= 1.1 + 1e-5
+    save_actor(actor, str(tmp_path / "ckpt"))
+    a2 = load_actor(RecurrentActor(), str(tmp_path / "ckpt"), map_location="cpu")
+    assert all(torch.equal(p.cpu(), q) for p, q in zip(actor.state_dict().values(), a2.state_dict().values()))
