@@ -257,7 +257,13 @@ typedef struct ozl_ekf_lee_args {
 } ozl_ekf_lee_args;
 int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* args, void* stream);
 
-/* Device address of the handle's step counter (uint64), for kernels that must follow it without a host round trip. */
+/* Device address of the handle's step counter, for kernels that must follow it without a host round trip.
+ * The counter is a 16-byte record of two uint64 words: word0 = base | (shift << 58), word1 = units, and
+ *     step = (word0 & (2^58 - 1)) + (word1 >> (word0 >> 58)).
+ * (Every step launch retires 2^shift work units with fire-and-forget reductions -- no last-block election on the step
+ * path; see ouzelum_b200/csrc/step_counter.cuh.)  Read both words with one 16-byte relaxed load; ozl_get_step_count does
+ * the same on the host.  The library's own consumers (ozl_pomdp_observation_dev, ozl_husky_step, ozl_ekf_lee_step) take
+ * this pointer. */
 int ozl_step_counter_ptr(ozl_env* env, const uint64_t** out);
 
 /* Sensor-fault model on an [n,d] f32 array.  Replaces POMDPWrapper.observation (isaacgymenvs/utils/POMDP.py:23-42).

@@ -160,7 +160,7 @@ __global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float 
                              float* __restrict__ out, const unsigned long long* __restrict__ step_ptr) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (step_ptr) step = *reinterpret_cast<const volatile unsigned long long*>(step_ptr);   // follow a device step counter
+    if (step_ptr) step = read_step(step_ptr);   // follow a handle's device step counter (3-word record, step_counter.cuh)
     bool blackout = false;
     if (mode == 1 || mode == 3) {
         const uint4 r = draw(seed, GLOBAL_ENV, step, P_FLICKER + (stream_id << 8));

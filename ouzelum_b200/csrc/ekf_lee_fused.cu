@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(OZL_EKF_BLOCK, OZL_EKF_MINB)
 ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const uint64_t step = *reinterpret_cast<const volatile unsigned long long*>(pl.ctrl);
+    const uint64_t step = read_step(pl.ctrl);
     const bool warm = (int64_t)step < a.convergence;                                     // :339
     const uint32_t genv = c.env_id_base + (uint32_t)i;
     const bool rst = a.reset[i] != 0;

@@ -10,7 +10,10 @@ namespace ozl {
 int set_error(const char* fmt, ...);   // stores a thread-local message, returns 1
 int check_cuda(cudaError_t e, const char* what);
 
-constexpr int kMetricSlots = 32;       // metric accumulators are striped over 32 slots (256 B apart) to spread L2 atomics
+#ifndef OZL_METRIC_SLOTS
+#define OZL_METRIC_SLOTS 32
+#endif
+constexpr int kMetricSlots = OZL_METRIC_SLOTS;   // metric accumulators are striped over this many slots (256 B apart) to spread L2 atomics
 constexpr int kMetricStride = 32;      // doubles per slot (16 used)
 
 // Private state of one handle: float4-packed planes, so one env == one 16-byte lane per plane.
@@ -30,7 +33,7 @@ constexpr int kTileBytes = kTile * (7 * 16 + 8);
 struct Planes {
     char* base;                 // arena
     int64_t plane4, plane2;     // OZL_TILED=0: byte strides of the float4 / float2 planes
-    unsigned long long* ctrl;   // [0] step counter, [1] block ticket, [2] TMA-kernel tile scheduler, [3] TMA-kernel CTAs done
+    unsigned long long* ctrl;   // [0..2] step-counter record {base, units, shift} (step_counter.cuh), [4] TMA-kernel tile scheduler, [5] TMA-kernel CTAs done
     double* metrics;            // kMetricSlots x kMetricStride
 };
 // k = 0..3: d0..d3, k = 4..6: s0..s2

@@ -58,12 +58,6 @@ __device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const 
     *plane4_ptr(pl, 6, i) = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
 }
 
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-
 // TMA 1-D bulk copy shared -> global (SASS: UBLKCP).  Used to write the block's contiguous [BLOCK,13] observation
 // tile with one instruction instead of a per-thread copy loop.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -80,48 +74,50 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Per-block metric reduction (K6): ballots/shuffles per warp -> smem -> one atomic per metric per block
-// into the block's slot.  Then the last block to finish (ticket) advances the step counter.
+// Episode statistics (K6) + step-counter retirement at the end of a block.
+// Metrics: one warp-level reduction per warp (redux / shuffles), then lane 0 adds the non-zero sums straight into the
+// warp's metric slot with fire-and-forget reductions (RED.ADD.F64): no shared memory, no block barrier, warps retire
+// independently.  The per-episode quantities (return, length, time-out / crash causes) are only reduced in warps where
+// an episode actually ended this step (warp-uniform branch on a ballot).
+// Metric slots: [0] sum reward [1] sum episode return [2] landed episodes [8] env-steps [9] episodes [10] sum episode
+// length [11] time-outs [12] crash(dist) [13] crash(z) [14] fault-active steps [15] resets applied.
 template <int BLOCK>
 __device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl, bool valid, const StepOut& o,
-                                               uint64_t step, uint32_t step_inc, double (*s_m)[11]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                               int n_here, unsigned long long units) {
     if (c.collect_metrics) {
         const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
         const bool done = valid && o.reset;
+        double* m = pl.metrics + ((blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) % kMetricSlots) * kMetricStride;
         const double srew = warp_sum(valid ? (double)o.rew : 0.0);
-        const double sret = warp_sum(done ? (double)o.ep_ret_done : 0.0);
-        const int slen = __reduce_add_sync(full, done ? (int)o.prog : 0);
-        const int n_valid = __popc(__ballot_sync(full, valid));
-        const int n_done = __popc(__ballot_sync(full, done));
-        const int n_to = __popc(__ballot_sync(full, valid && o.timeout));
-        const int n_cd = __popc(__ballot_sync(full, valid && o.crash_dist));
-        const int n_cz = __popc(__ballot_sync(full, valid && o.crash_z));
-        const int n_fa = __popc(__ballot_sync(full, valid && o.fault_active));
-        const int n_rs = __popc(__ballot_sync(full, valid && o.did_reset));
-        const int n_ld = __popc(__ballot_sync(full, valid && o.landed_episode));
+        // three 1-bit flags per lane in 8-bit fields (<= 32 per field)
+        const uint32_t pk = __reduce_add_sync(full, valid ? ((uint32_t)o.fault_active | ((uint32_t)o.did_reset << 8) |
+                                                             ((uint32_t)o.landed_episode << 16)) : 0u);
+        const unsigned done_mask = __ballot_sync(full, done);
         if (lane == 0) {
-            s_m[warp][0] = srew; s_m[warp][1] = sret; s_m[warp][2] = n_valid; s_m[warp][3] = n_done;
-            s_m[warp][4] = slen; s_m[warp][5] = n_to; s_m[warp][6] = n_cd; s_m[warp][7] = n_cz;
-            s_m[warp][8] = n_fa; s_m[warp][9] = n_rs; s_m[warp][10] = n_ld;
+            if (srew != 0.0) atomicAdd(m + 0, srew);
+            if (pk & 0xFFu) atomicAdd(m + 14, (double)(pk & 0xFFu));
+            if ((pk >> 8) & 0xFFu) atomicAdd(m + 15, (double)((pk >> 8) & 0xFFu));
+            if (pk >> 16) atomicAdd(m + 2, (double)(pk >> 16));
         }
-        __syncthreads();
-        if (threadIdx.x < 11) {
-            double v = 0.0;
-#pragma unroll
-            for (int wv = 0; wv < BLOCK / 32; ++wv) v += s_m[wv][threadIdx.x];
-            const int idx = threadIdx.x < 2 ? threadIdx.x : (threadIdx.x == 10 ? 2 : threadIdx.x + 6);   // sums [0,1], landed [2], counts [8..15]
-            if (v != 0.0) atomicAdd(pl.metrics + (blockIdx.x % kMetricSlots) * kMetricStride + idx, v);
+        if (done_mask) {
+            const double sret = warp_sum(done ? (double)o.ep_ret_done : 0.0);
+            const int slen = __reduce_add_sync(full, done ? (int)o.prog : 0);
+            const uint32_t pe = __reduce_add_sync(full, done ? ((uint32_t)o.timeout | ((uint32_t)o.crash_dist << 8) |
+                                                                ((uint32_t)o.crash_z << 16)) : 0u);
+            if (lane == 0) {
+                if (sret != 0.0) atomicAdd(m + 1, sret);
+                atomicAdd(m + 9, (double)__popc(done_mask));
+                atomicAdd(m + 10, (double)slen);
+                if (pe & 0xFFu) atomicAdd(m + 11, (double)(pe & 0xFFu));
+                if ((pe >> 8) & 0xFFu) atomicAdd(m + 12, (double)((pe >> 8) & 0xFFu));
+                if (pe >> 16) atomicAdd(m + 13, (double)(pe >> 16));
+            }
         }
+        if (threadIdx.x == 0 && n_here > 0) atomicAdd(m + 8, (double)n_here);
     }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long t = atomicAdd(pl.ctrl + 1, 1ull);
-        if (t == (unsigned long long)gridDim.x - 1ull) {   // every other block has already read ctrl[0]
-            pl.ctrl[1] = 0ull;
-            pl.ctrl[0] = step + step_inc;
-        }
-    }
+    // the caller has passed a block barrier after every thread consumed its copy of the step index (step_counter.cuh)
+    if (threadIdx.x == 0) retire_units(pl.ctrl, units);
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -132,7 +128,7 @@ __device__ __forceinline__ void block_epilogue(const DevCfg& c, const Planes& pl
 #define OZL_STEP_BLOCK 128
 #endif
 #ifndef OZL_STEP_MINB
-#define OZL_STEP_MINB 8
+#define OZL_STEP_MINB 7
 #endif
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
@@ -141,24 +137,31 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
                  const int act_mode, uint8_t* __restrict__ done_u8, const int obs_bulk, const int64_t env0) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
-    __shared__ double s_m[BLOCK / 32][11];
+    __shared__ uint64_t s_step;
 
     const int64_t base = env0 + (int64_t)blockIdx.x * BLOCK;
     const int64_t i = base + threadIdx.x;
     const bool valid = i < c.num_envs;
-    const uint64_t step = ld_relaxed(pl.ctrl);
+    if (threadIdx.x == 0) s_step = read_step(pl.ctrl);     // one request per block (all of them hit the same L2 slice)
 
     StepOut o;
     o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
     o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
 
+    // all loads issued up front: 9 x 128-bit + 2 x 64-bit per env in flight while the block waits for the step index
+    Loaded L;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t prog = 0;
+    bool rst = false;
     if (valid) {
-        // all loads issued up front: 9 x 128-bit + 2 x 64-bit per env in flight
-        Loaded L;
         load_env(pl, i, L);
-        const float4 a4 = __ldg(actions + i);
-        const int64_t prog = progress[i];
-        const bool rst = reset[i] != 0;
+        a4 = __ldg(actions + i);
+        prog = progress[i];
+        rst = reset[i] != 0;
+    }
+    __syncthreads();
+    const uint64_t step = s_step;
+    if (valid) {
         Env e;
         unpack(L, e);
         float tnew[3];
@@ -186,9 +189,9 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
 #endif
     __syncthreads();
     // [N,13] row-major observation tile of this block is contiguous: write it with full 16-byte lanes
+    const int64_t remaining = c.num_envs - base;
+    const int n_here = remaining < BLOCK ? (int)remaining : BLOCK;
     {
-        const int64_t remaining = c.num_envs - base;
-        const int n_here = remaining < BLOCK ? (int)remaining : BLOCK;
         float* dst = obs + base * 13;
         const int nflt = n_here * 13;
         if ((nflt & 3) == 0) {   // base*13*4 bytes is 16-byte aligned whenever BLOCK % 4 == 0
@@ -213,7 +216,9 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
             for (int k = threadIdx.x; k < nflt; k += BLOCK) dst[k] = s_obs[k];
         }
     }
-    block_epilogue<BLOCK>(c, pl, valid, o, step, 1u, s_m);
+    // one work unit per block; block 0 of the full-range launch also retires the padding (env0 != 0: ragged-tail launch
+    // behind the TMA kernel, which has retired the padding already)
+    block_epilogue<BLOCK>(c, pl, valid, o, n_here, 1ull + ((blockIdx.x == 0 && env0 == 0) ? (unsigned long long)c.step_pad : 0ull));
 #if OZL_OBS_BULK
     if (threadIdx.x == 0) bulk_wait_read_all();   // s_obs must stay alive until the bulk copy has read it
 #endif
@@ -265,17 +270,17 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
 __global__ void __launch_bounds__(kTile, OZL_TMA_MINB)
 quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                      float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
-                     uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const int64_t full_tiles,
-                     const int do_ticket) {
+                     uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const int64_t full_tiles) {
     __shared__ __align__(128) unsigned char s_stage[kTmaStageBytes];
     __shared__ __align__(16) float s_obs[kTile * 13];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ double s_m[kTile / 32][11];
     const int tid = threadIdx.x;
-    const uint64_t step = ld_relaxed(pl.ctrl);
-    const bool blackout = flicker_blackout(step, c);
-    if (tid == 0) mbar_init(&s_bar, 1);
+    __shared__ uint64_t s_step;
+    if (tid == 0) { s_step = read_step(pl.ctrl); mbar_init(&s_bar, 1); }
     __syncthreads();
+    const uint64_t step = s_step;
+    const bool blackout = flicker_blackout(step, c);
 
     auto issue = [&](int64_t tile) {            // thread 0 only
         mbar_expect_tx(&s_bar, kTmaStageBytes);
@@ -284,14 +289,14 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         bulk_load_g2s(s_stage + kTmaProgOff, progress + tile * kTile, kTile * 8, &s_bar);
         bulk_load_g2s(s_stage + kTmaRstOff, reset + tile * kTile, kTile * 8, &s_bar);
     };
-    // dynamic tile scheduler: the first tile of a CTA is its block index, further tiles come from a device counter (ctrl[2]);
+    // dynamic tile scheduler: the first tile of a CTA is its block index, further tiles come from a device counter (ctrl[4]);
     // thread 0 requests the index one iteration ahead so the atomic's round trip never sits on the critical path
     __shared__ long long s_next;
     int64_t tile = blockIdx.x;
     long long nxt = 0;
     if (tid == 0) {
         if (tile < full_tiles) issue(tile);
-        nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 2, 1ull);
+        nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
     }
 
     // metric accumulators over all tiles of this CTA (per-thread counts packed 16 bits each; the host keeps the average number of
@@ -321,7 +326,7 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         if (tid == 0) {
             if (next < full_tiles) {
                 issue(next);
-                nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 2, 1ull);
+                nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
             }
         }
 
@@ -380,14 +385,15 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
     }
     if (tid == 0) {
         bulk_wait_read_all();
-        // the step counter is advanced by the last CTA of the LAST launch of a step: this kernel when N is a whole number of
-        // tiles, otherwise the one-block tail launch of quad_step_kernel that follows it on the stream
+        // step counter: one work unit per tile processed (+ the padding, CTA 0); a ragged tail is retired by the one-block
+        // launch of quad_step_kernel that follows on the stream
+        retire_units(pl.ctrl, (unsigned long long)m_valid + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
+        // last CTA of this launch re-arms the tile scheduler (once per persistent CTA: off the per-tile path)
         __threadfence();
-        const unsigned long long t = atomicAdd(pl.ctrl + 3, 1ull);
-        if (t == (unsigned long long)gridDim.x - 1ull) {      // last CTA of this launch: re-arm the tile scheduler
-            pl.ctrl[3] = 0ull;
-            pl.ctrl[2] = 0ull;
-            if (do_ticket) pl.ctrl[0] = step + 1ull;
+        const unsigned long long t = atomicAdd(pl.ctrl + 5, 1ull);
+        if (t == (unsigned long long)gridDim.x - 1ull) {
+            pl.ctrl[5] = 0ull;
+            pl.ctrl[4] = 0ull;
         }
     }
 }
@@ -398,10 +404,12 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 quad_rollout_kernel(const DevCfg c, const Planes pl, int K, float* __restrict__ obs, float* __restrict__ rew,
                     int64_t* __restrict__ reset, int64_t* __restrict__ progress) {
-    __shared__ double s_m[BLOCK / 32][11];
     const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = i < c.num_envs;
-    const uint64_t step0 = ld_relaxed(pl.ctrl);
+    __shared__ uint64_t s_step;
+    if (threadIdx.x == 0) s_step = read_step(pl.ctrl);
+    __syncthreads();
+    const uint64_t step0 = s_step;
     StepOut o;
     o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
     o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
@@ -462,7 +470,11 @@ quad_rollout_kernel(const DevCfg c, const Planes pl, int K, float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 13; ++j) obs[i * 13 + j] = o.obs[j];
     }
-    block_epilogue<BLOCK>(c, pl, valid, o, step0, (uint32_t)K, s_m);
+    // the launch retires ONE step's worth of units; the host adds the other K - 1 steps to the counter base afterwards
+    __syncthreads();
+    const int64_t remaining = c.num_envs - (int64_t)blockIdx.x * BLOCK;
+    block_epilogue<BLOCK>(c, pl, valid, o, remaining < BLOCK ? (int)remaining : BLOCK,
+                          1ull + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
 }
 
 // ------------------------------------------------------------------------------------------------ state access
@@ -540,7 +552,7 @@ __global__ void set_params_kernel(const Planes pl, int64_t n, const float* param
 __global__ void apply_resets_kernel(const DevCfg c, const Planes pl, const int64_t* __restrict__ reset) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.num_envs || reset[i] == 0) return;
-    const uint64_t step = ld_relaxed(pl.ctrl);
+    const uint64_t step = read_step(pl.ctrl);
     Loaded L;
     load_env(pl, i, L);
     Env e;
@@ -580,7 +592,10 @@ __global__ void apply_resets_kernel(const DevCfg c, const Planes pl, const int64
 
 __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { pl.ctrl[0] = 0ull; pl.ctrl[1] = 0ull; pl.ctrl[2] = 0ull; pl.ctrl[3] = 0ull; }
+    if (i == 0) {
+        pl.ctrl[0] = step_word0_dev(0ull, c.step_shift); pl.ctrl[1] = 0ull;
+        pl.ctrl[4] = 0ull; pl.ctrl[5] = 0ull;
+    }
     if (i < kMetricSlots * kMetricStride) pl.metrics[i] = 0.0;
     if (i >= c.num_envs) return;
     Env e;
@@ -597,18 +612,20 @@ __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     store_static(pl, i, e);
 }
 
+// 16 warps, one per metric: lanes stride over the slots, then a warp reduction
 __global__ void metrics_read_kernel(const Planes pl, double* out16, int clear) {
-    const int j = threadIdx.x;
-    if (j >= 16) return;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
-    for (int s = 0; s < kMetricSlots; ++s) {
+    for (int s = lane; s < kMetricSlots; s += 32) {
         v += pl.metrics[s * kMetricStride + j];
         if (clear) pl.metrics[s * kMetricStride + j] = 0.0;
     }
-    out16[j] = v;
+    v = warp_sum(v);
+    if (lane == 0) out16[j] = v;
 }
 
-__global__ void set_step_kernel(const Planes pl, unsigned long long v) { pl.ctrl[0] = v; pl.ctrl[1] = 0ull; }
+__global__ void set_step_kernel(const Planes pl, unsigned long long word0) { pl.ctrl[0] = word0; pl.ctrl[1] = 0ull; }
+__global__ void add_steps_kernel(const Planes pl, unsigned long long k) { pl.ctrl[0] += k; }
 
 }  // namespace ozl
 
@@ -660,6 +677,13 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
         while ((1ull << l) < dd) ++l;
         d.period_shift = 31 + l;
         d.period_magic = (uint32_t)(((1ull << (31 + l)) + dd - 1) / dd);
+    }
+    {   // step counter (step_counter.cuh): one work unit per 128-env tile, padded to a power of two per step
+        const uint64_t tiles = ((uint64_t)c.num_envs + kTile - 1) / kTile;
+        uint32_t l = 0;
+        while ((1ull << l) < tiles) ++l;
+        d.step_shift = l;
+        d.step_pad = (uint32_t)((1ull << l) - tiles);
     }
     d.sinc_c1 = (float)(-1.0 / 6.0); d.sinc_c2 = (float)(1.0 / 120.0);
     d.cos_c1 = -0.5f; d.cos_c2 = (float)(1.0 / 24.0); d.cos_c3 = (float)(-1.0 / 720.0);
@@ -738,9 +762,10 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     derive_dev_cfg(*cfg, e->dev);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets >= 3 tiles (measured crossover ~300k envs) (override: OZL_TMA_MIN_TILES, 0 = never)
+    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets ~4.75 tiles (measured crossover on B200: generic
+        // 21.5 vs 22.3 us at 393216 envs, 31.6 vs 29.4 us at 524288) (override: OZL_TMA_MIN_TILES, 0 = never)
         const char* ev = getenv("OZL_TMA_MIN_TILES");
-        e->tma_min_tiles = ev ? atoll(ev) : 3ll * prop.multiProcessorCount * OZL_TMA_MINB;
+        e->tma_min_tiles = ev ? atoll(ev) : (19ll * prop.multiProcessorCount * OZL_TMA_MINB) / 4;
     }
     const size_t n = (size_t)cfg->num_envs;
     const size_t tiles = (n + kTile - 1) / kTile;
@@ -784,6 +809,7 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 
 // Block size: 128 threads keeps >= 1 block on every SM down to ~19k envs and lets 16k-env launches use 128 SMs.
 constexpr int kStepBlock = OZL_STEP_BLOCK;
+static_assert(kStepBlock == kTile, "the step counter retires one work unit per 128-env tile == one block of the generic kernel");
 
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
@@ -803,7 +829,7 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         { static const char* eg = getenv("OZL_TMA_GRID"); if (eg && atoi(eg) > 0 && (int64_t)atoi(eg) <= full_tiles) grid = (unsigned)atoi(eg); }   // tuning aid
         while ((full_tiles + grid - 1) / grid > 8192) grid *= 2;     // 16-bit packed metric counters: keep tiles per CTA far below 65535
         quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
-                                                      ep_ret, full_tiles, tail == 0 ? 1 : 0);
+                                                      ep_ret, full_tiles);
         if (check_cuda(cudaGetLastError(), "quad_step_tma_kernel")) return 1;
         if (tail)
             quad_step_kernel<kStepBlock><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress,
@@ -854,7 +880,9 @@ extern "C" int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int6
     if (!obs || !rew || !reset || !progress) return set_error("ozl_rollout: NULL buffer");
     quad_rollout_kernel<kStepBlock><<<blocks_for(env->cfg.num_envs, kStepBlock), kStepBlock, 0, st>>>(
         env->dev, env->pl, K, obs, rew, reset, progress);
-    return check_cuda(cudaGetLastError(), "quad_rollout_kernel");
+    if (check_cuda(cudaGetLastError(), "quad_rollout_kernel")) return 1;
+    if (K > 1) add_steps_kernel<<<1, 1, 0, st>>>(env->pl, (unsigned long long)(K - 1));
+    return check_cuda(cudaGetLastError(), "add_steps_kernel");
 }
 
 extern "C" int ozl_get_state(ozl_env* env, float* root13, float* thrust4, float* target3, float* ep_ret, void* stream) {
@@ -882,21 +910,22 @@ extern "C" int ozl_set_params(ozl_env* env, const float* params7, const int32_t*
 extern "C" int ozl_get_step_count(ozl_env* env, uint64_t* out, void* stream) {
     OZL_ENV_CHECK("ozl_get_step_count");
     if (!out) return set_error("ozl_get_step_count: out is NULL");
-    unsigned long long v = 0;
-    if (check_cuda(cudaMemcpyAsync(&v, env->pl.ctrl, sizeof(v), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) return 1;
+    unsigned long long w[2] = {0, 0};
+    if (check_cuda(cudaMemcpyAsync(w, env->pl.ctrl, sizeof(w), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) return 1;
     if (check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return 1;
-    *out = v;
+    *out = step_from_words(w);
     return 0;
 }
 extern "C" int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream) {
     OZL_ENV_CHECK("ozl_set_step_count");
-    set_step_kernel<<<1, 1, 0, st>>>(env->pl, (unsigned long long)value);
+    if (value > kStepBaseMask) return set_error("ozl_set_step_count: value out of range");
+    set_step_kernel<<<1, 1, 0, st>>>(env->pl, step_word0((unsigned long long)value, env->dev.step_shift));
     return check_cuda(cudaGetLastError(), "set_step_kernel");
 }
 
 extern "C" int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream) {
     OZL_ENV_CHECK("ozl_metrics_read");
     if (!out16) return set_error("ozl_metrics_read: out16 is NULL");
-    metrics_read_kernel<<<1, 32, 0, st>>>(env->pl, out16, clear);
+    metrics_read_kernel<<<1, 16 * 32, 0, st>>>(env->pl, out16, clear);
     return check_cuda(cudaGetLastError(), "metrics_read_kernel");
 }

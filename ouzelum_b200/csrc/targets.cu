@@ -63,7 +63,7 @@ husky_step_kernel(const HuskyArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const uint32_t genv = a.env_id_base + (uint32_t)i;
-    const uint64_t step = a.step_ptr ? *reinterpret_cast<const volatile unsigned long long*>(a.step_ptr) : a.step;
+    const uint64_t step = a.step_ptr ? read_step(a.step_ptr) : a.step;
     float4 p = a.pose[i];
     int2 id = a.idx[i];
     // re-spawn a strayed vehicle when its drone resets (landing.py:263-270)

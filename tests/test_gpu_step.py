@@ -174,3 +174,38 @@ def test_kernel_vs_c_oracle_long_rollout():
             assert np.array_equal(b["rew"].cpu().numpy(), co.rew_buf), t
     assert np.array_equal(sim.get_state()["root"].cpu().numpy(), co.root)
     assert int(co.timeout_buf.sum()) >= 0 and int(sim.metrics()[11].item()) > 0      # time-outs happened (max_len 150)
+
+
+@pytest.mark.parametrize("n", [1, 129, 640, 4099])
+def test_device_step_counter_record(n):
+    """The device step counter (csrc/step_counter.cuh: base + (units >> shift), one unit retired per 128-env block plus the
+    power-of-two padding) advances by exactly one per step launch for tile counts that are / are not powers of two,
+    by K per K-step roll-out, survives set / get, and stays in step inside a replayed CUDA graph."""
+    sim, _, b = _mk(n, seed=5)
+    a = torch.zeros(n, 4, device="cuda")
+    args = (b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+    for k in range(1, 6):
+        sim.step(a, *args)
+        assert sim.step_count == k
+    sim.step_count = 10 ** 12
+    assert sim.step_count == 10 ** 12
+    sim.step(a, *args)
+    assert sim.step_count == 10 ** 12 + 1
+    sim.rollout(7, b["obs"], b["rew"], b["reset"], b["progress"])
+    assert sim.step_count == 10 ** 12 + 8
+    sim.step_wrench(a, None, *args)
+    sim.apply_resets(b["reset"])                      # reads the counter, must not advance it
+    assert sim.step_count == 10 ** 12 + 9
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        sim.step(a, *args)
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(3):                        # odd number of launches per replay
+                sim.step(a, *args)
+    torch.cuda.current_stream().wait_stream(s)
+    c0 = sim.step_count
+    for _ in range(4):
+        g.replay()
+    assert sim.step_count == c0 + 12
