@@ -7,6 +7,7 @@
 //     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
 //   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
 #include "internal.h"
+#include "bulk_copy.cuh"
 #include "filters.cuh"
 #include "glue.cuh"
 #include "lee_control.cuh"
@@ -37,99 +38,152 @@ struct EkfLeeArgs {
 #define OZL_EKF_BLOCK 128
 #endif
 #ifndef OZL_EKF_MINB
-#define OZL_EKF_MINB 4   // 128 regs: 4 CTAs/SM so 65536 envs fit one wave (measured 44 -> 39 us/step despite ~0.5 KB of spills)
+#define OZL_EKF_MINB 4
 #endif
-__global__ void __launch_bounds__(OZL_EKF_BLOCK, OZL_EKF_MINB)
-ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const uint64_t step = read_step(pl.ctrl);
+constexpr int kEkfBlock = OZL_EKF_BLOCK;
+
+// Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA):
+//   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by thread 0 with 81 TMA
+//     bulk copies (512 B each, one per plane) completing on an mbarrier, issued before anything else: the 41 KB of loads
+//     fly while every thread runs the sensor front-end and the float64 attitude EKF out of registers
+//   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared)
+//   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
+//   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
+__global__ void __launch_bounds__(kEkfBlock, OZL_EKF_MINB)
+ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma) {
+    __shared__ __align__(128) float s_P[81 * kEkfBlock];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint64_t s_step;
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kEkfBlock;
+    const int64_t i = base + tid;
+    const bool valid = i < a.n;
+    const int n_here = (a.n - base) < kEkfBlock ? (int)(a.n - base) : kEkfBlock;
+    if (tid == 0) {
+        s_step = read_step(pl.ctrl);
+        if (use_tma) mbar_init(&s_bar, 1);
+    }
+    __syncthreads();
+    if (use_tma) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)n_here * 4u;
+            mbar_expect_tx(&s_bar, 81u * bytes);
+#pragma unroll 1
+            for (int k = 0; k < 81; ++k) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
+        }
+    } else if (valid) {
+#pragma unroll 9
+        for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
+    }
+    const uint64_t step = s_step;
     const bool warm = (int64_t)step < a.convergence;                                     // :339
     const uint32_t genv = c.env_id_base + (uint32_t)i;
-    const bool rst = a.reset[i] != 0;
-    // ---- true root state (post reset_idx)
-    float p[3], q[4], v[3], w[3];
-    if (rst) {
-        const uint4 r = draw(c.seed, genv, step, P_SPAWN);
-        p[0] = c.spawn_base[0] + (c.spawn_range[0] * u01(r.x) + c.spawn_lo[0]);
-        p[1] = c.spawn_base[1] + (c.spawn_range[1] * u01(r.y) + c.spawn_lo[1]);
-        p[2] = c.spawn_base[2] + (c.spawn_range[2] * u01(r.z) + c.spawn_lo[2]);
-        q[0] = q[1] = q[2] = 0.f; q[3] = 1.f;
-        for (int j = 0; j < 3; ++j) { v[j] = 0.f; w[j] = 0.f; }
-    } else {
-        const float4 d0 = *plane4_ptr(pl, 0, i), d1 = *plane4_ptr(pl, 1, i), d2 = *plane4_ptr(pl, 2, i);
-        const float wz = plane4_ptr(pl, 3, i)->x;
-        p[0] = d0.x; p[1] = d0.y; p[2] = d0.z; q[0] = d0.w; q[1] = d1.x; q[2] = d1.y; q[3] = d1.z;
-        v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz;
+    // live across the block barrier that precedes the drain of the covariance tile: controller inputs
+    float q[4], w[3], est_p[3], est_v[3], cmd[4];
+    if (valid) {
+        const bool rst = a.reset[i] != 0;
+        // ---- true root state (post reset_idx)
+        float p[3], v[3];
+        if (rst) {
+            const uint4 r = draw(c.seed, genv, step, P_SPAWN);
+            p[0] = c.spawn_base[0] + (c.spawn_range[0] * u01(r.x) + c.spawn_lo[0]);
+            p[1] = c.spawn_base[1] + (c.spawn_range[1] * u01(r.y) + c.spawn_lo[1]);
+            p[2] = c.spawn_base[2] + (c.spawn_range[2] * u01(r.z) + c.spawn_lo[2]);
+            q[0] = q[1] = q[2] = 0.f; q[3] = 1.f;
+            for (int j = 0; j < 3; ++j) { v[j] = 0.f; w[j] = 0.f; }
+        } else {
+            const float4 d0 = *plane4_ptr(pl, 0, i), d1 = *plane4_ptr(pl, 1, i), d2 = *plane4_ptr(pl, 2, i);
+            const float wz = plane4_ptr(pl, 3, i)->x;
+            p[0] = d0.x; p[1] = d0.y; p[2] = d0.z; q[0] = d0.w; q[1] = d1.x; q[2] = d1.y; q[3] = d1.z;
+            v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz;
+        }
+        // ---- sensor front-end (:345-346,366-375,397-406)
+        FaultCfg f = a.f;
+        f.step = step;
+        if (warm) f.mode = 0;
+        float acc[3], gyr[3], ang[4], pos[3], vel[3];
+        for (int j = 0; j < 3; ++j) {
+            acc[j] = (v[j] - a.prev_linvel[i * 3 + j]) / a.dt;
+            gyr[j] = w[j]; pos[j] = p[j]; vel[j] = v[j];
+            a.prev_linvel[i * 3 + j] = v[j];                                              // :454
+        }
+        acc[2] = acc[2] + 9.8f;
+        for (int j = 0; j < 4; ++j) ang[j] = q[j];
+        sensor_fault(f, genv, 1, false, gyr, 3);
+        sensor_fault(f, genv, 3, true, ang, 4);
+        sensor_fault(f, genv, 4, false, acc, 3);
+        sensor_fault(f, genv, 5, false, pos, 3);
+        sensor_fault(f, genv, 6, false, vel, 3);
+        // ---- attitude EKF (:348-352,378-391), float64 in registers
+        float q32[4];
+        {
+            EKF4 s;
+            if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
+            else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
+            for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
+            const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
+            const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
+            ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
+            for (int k = 0; k < 4; ++k) { a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
+            for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4];
+        }
+        // ---- PV filter (:353-358,397-444) on the shared-memory covariance tile
+        {
+            PVShared<kEkfBlock> s;
+            s.P = s_P + tid;
+            for (int k = 0; k < 9; ++k) s.x[k] = a.pv_x[(int64_t)k * a.n + i];
+            if (rst) { for (int k = 0; k < 3; ++k) { s.x[k] = p[k]; s.x[3 + k] = v[k]; s.x[6 + k] = 0.f; } }
+            const float qt[4] = {q[3], q[0], q[1], q[2]};
+            if (use_tma) mbar_wait(&s_bar, 0);                    // the covariance tile has landed
+            pv_predict(s, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
+            const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n + (uint64_t)i;   // shared counters (:425-440)
+            if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(s, pos, a.pos_var);
+            const float zero3[3] = {0.f, 0.f, 0.f};
+            if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(s, vel, zero3);  // gps_var=None => R = 0
+            for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = s.x[kk];
+            for (int kk = 0; kk < 3; ++kk) { est_p[kk] = s.x[kk]; est_v[kk] = s.x[3 + kk]; }
+        }
+        if (!use_tma) {
+#pragma unroll 9
+            for (int k = 0; k < 81; ++k) a.pv_P[(int64_t)k * a.n + i] = s_P[k * kEkfBlock + tid];
+        }
+        // (the TMA drain of the tile is issued below, after the block barrier, and overlaps the controller)
+        // ---- waypoint + controller (:458-529)
+        const float t[3] = {a.target[i * 3], a.target[i * 3 + 1], a.target[i * 3 + 2]};
+        float wp[3] = {a.waypoint[i * 3], a.waypoint[i * 3 + 1], a.waypoint[i * 3 + 2]};
+        waypoint_update(p, t, wp, warm);
+        for (int j = 0; j < 3; ++j) a.waypoint[i * 3 + j] = wp[j];
+        if (a.est13) {
+            float* e = a.est13 + i * 13;
+            for (int j = 0; j < 3; ++j) { e[j] = warm ? p[j] : est_p[j]; e[7 + j] = warm ? v[j] : est_v[j]; e[10 + j] = w[j]; }
+            for (int j = 0; j < 4; ++j) e[3 + j] = q[j];
+        }
+        if (a.cmd4) a.cmd4[i] = make_float4(wp[0], wp[1], wp[2], 0.0f);
+        cmd[0] = wp[0] * a.g.scale[0]; cmd[1] = wp[1] * a.g.scale[1]; cmd[2] = wp[2] * a.g.scale[2]; cmd[3] = 0.0f;
     }
-    // ---- sensor front-end (:345-346,366-375,397-406)
-    FaultCfg f = a.f;
-    f.step = step;
-    if (warm) f.mode = 0;
-    float acc[3], gyr[3], ang[4], pos[3], vel[3];
-    for (int j = 0; j < 3; ++j) {
-        acc[j] = (v[j] - a.prev_linvel[i * 3 + j]) / a.dt;
-        gyr[j] = w[j]; pos[j] = p[j]; vel[j] = v[j];
-        a.prev_linvel[i * 3 + j] = v[j];                                                  // :454
+    if (use_tma) {
+        // drain: every thread's filter writes are made visible to the async proxy, then thread 0 issues the bulk stores
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)n_here * 4u;
+#pragma unroll 1
+            for (int k = 0; k < 81; ++k) bulk_store_s2g_issue(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, bytes);
+            bulk_commit();
+        }
     }
-    acc[2] = acc[2] + 9.8f;
-    for (int j = 0; j < 4; ++j) ang[j] = q[j];
-    sensor_fault(f, genv, 1, false, gyr, 3);
-    sensor_fault(f, genv, 3, true, ang, 4);
-    sensor_fault(f, genv, 4, false, acc, 3);
-    sensor_fault(f, genv, 5, false, pos, 3);
-    sensor_fault(f, genv, 6, false, vel, 3);
-    // ---- attitude EKF (:348-352,378-391)
-    float q32[4];
-    {
-        EKF4 s;
-        if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
-        else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
-        for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
-        const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
-        const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
-        ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
-        for (int k = 0; k < 4; ++k) { a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
-        for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4];
+    if (valid) {
+        float4 wr;
+        if (warm) {
+            wr = make_float4(a.hover, 0.f, 0.f, 0.f);                                     // :526-528
+        } else {
+            float th, tq[3];
+            lee_control(LEE_POSITION, est_p, q, est_v, w, cmd, a.g, th, tq);               // :493-499
+            wr = make_float4(a.mg * th, tq[0], tq[1], tq[2]);                              // :504-505
+        }
+        a.wrench[i] = wr;
     }
-    // ---- PV filter (:353-358,397-444)
-    float est_p[3], est_v[3];
-    {
-        PV s;
-        for (int k = 0; k < 9; ++k) s.x[k] = a.pv_x[(int64_t)k * a.n + i];
-        for (int k = 0; k < 81; ++k) s.P[k / 9][k % 9] = a.pv_P[(int64_t)k * a.n + i];
-        if (rst) { for (int k = 0; k < 3; ++k) { s.x[k] = p[k]; s.x[3 + k] = v[k]; s.x[6 + k] = 0.f; } }
-        const float qt[4] = {q[3], q[0], q[1], q[2]};
-        pv_predict(s, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
-        const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n + (uint64_t)i;   // shared counters (:425-440)
-        if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(s, pos, a.pos_var);
-        const float zero3[3] = {0.f, 0.f, 0.f};
-        if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(s, vel, zero3);  // gps_var=None => R = 0
-        for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = s.x[kk];
-        for (int kk = 0; kk < 81; ++kk) a.pv_P[(int64_t)kk * a.n + i] = s.P[kk / 9][kk % 9];
-        for (int kk = 0; kk < 3; ++kk) { est_p[kk] = s.x[kk]; est_v[kk] = s.x[3 + kk]; }
-    }
-    // ---- waypoint + controller (:458-529)
-    const float t[3] = {a.target[i * 3], a.target[i * 3 + 1], a.target[i * 3 + 2]};
-    float wp[3] = {a.waypoint[i * 3], a.waypoint[i * 3 + 1], a.waypoint[i * 3 + 2]};
-    waypoint_update(p, t, wp, warm);
-    for (int j = 0; j < 3; ++j) a.waypoint[i * 3 + j] = wp[j];
-    const float cmd[4] = {wp[0] * a.g.scale[0], wp[1] * a.g.scale[1], wp[2] * a.g.scale[2], 0.0f};
-    float4 wr;
-    if (warm) {
-        wr = make_float4(a.hover, 0.f, 0.f, 0.f);                                         // :526-528
-    } else {
-        float th, tq[3];
-        lee_control(LEE_POSITION, est_p, q, est_v, w, cmd, a.g, th, tq);                   // :493-499
-        wr = make_float4(a.mg * th, tq[0], tq[1], tq[2]);                                  // :504-505
-    }
-    a.wrench[i] = wr;
-    if (a.est13) {
-        float* e = a.est13 + i * 13;
-        for (int j = 0; j < 3; ++j) { e[j] = warm ? p[j] : est_p[j]; e[7 + j] = warm ? v[j] : est_v[j]; e[10 + j] = w[j]; }
-        for (int j = 0; j < 4; ++j) e[3 + j] = q[j];
-    }
-    if (a.cmd4) a.cmd4[i] = make_float4(wp[0], wp[1], wp[2], 0.0f);
+    if (use_tma && tid == 0) bulk_wait_read_all();      // the tile must stay alive until the bulk stores have read it
 }
 
 }  // namespace ozl
@@ -161,7 +215,9 @@ extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* 
     a.ekf_Dt = in->ekf_Dt; a.ekf_g_noise = in->ekf_g_noise;
     for (int k = 0; k < 3; ++k) { a.g.kP[k] = in->gains16[k]; a.g.kV[k] = in->gains16[3 + k]; a.g.kR[k] = in->gains16[6 + k]; a.g.kO[k] = in->gains16[9 + k]; }
     for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
-    ekf_lee_fused_kernel<<<(unsigned)((a.n + OZL_EKF_BLOCK - 1) / OZL_EKF_BLOCK), OZL_EKF_BLOCK, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a);
+    // TMA path: every [k][N] plane slice of a block must start on a 16-byte boundary and be a multiple of 16 bytes long
+    const int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);
+    ekf_lee_fused_kernel<<<(unsigned)((a.n + kEkfBlock - 1) / kEkfBlock), kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma);
     return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
 }
 

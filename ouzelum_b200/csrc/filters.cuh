@@ -166,6 +166,162 @@ __device__ __forceinline__ void pv_correct(PV& s, const float z[3], const float 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K3, covariance in shared memory
+// Same arithmetic as pv_predict / pv_correct (same operations in the same order), but the 9x9 covariance of the thread's env
+// lives in SHARED memory -- element (r,c) of thread t at P[(r*9 + c) * STRIDE + t], conflict-free -- and the loops over
+// columns / rows stay ROLLED.  The register variants above unroll into ~2000 straight-line instructions holding 81 + ~50 live
+// floats per thread (168 registers, 3-4 CTAs/SM, instruction-cache misses: "no_instruction" was 19 % of the stall cycles of
+// the fused kernel); this form needs ~60 registers for the filter and ~250 instructions of loop body.
+template <int STRIDE>
+struct PVShared {
+    float x[9];
+    float* P;                              // this thread's column of the block's [81][STRIDE] covariance tile
+    __device__ __forceinline__ float& at(int r, int c) { return P[(r * 9 + c) * STRIDE]; }
+};
+
+template <int STRIDE>
+__device__ __forceinline__ void pv_predict(PVShared<STRIDE>& s, const float acc[3], const float q_wxyz[4], float dt, float dt2,
+                                           const float acc_var[3]) {
+    float Rq[3][3], R[3][3], A[3][3], B[3][3];
+    pv_quat_to_R(q_wxyz[0], q_wxyz[1], q_wxyz[2], q_wxyz[3], Rq);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            R[i][j] = Rq[j][i];
+            A[i][j] = R[i][j] * dt;
+            B[i][j] = (R[i][j] * dt2) * 0.5f;
+        }
+    float u[3], np_[3], nv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u[i] = acc[i] - s.x[6 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float fp = s.x[i], fv = 0.f, gp = 0.f, gv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            fp += A[i][j] * s.x[3 + j];
+            fv += R[i][j] * s.x[3 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            fp += B[i][j] * s.x[6 + j];
+            fv += A[i][j] * s.x[6 + j];
+            gp += B[i][j] * u[j];
+            gv += A[i][j] * u[j];
+        }
+        np_[i] = fp + gp;
+        nv[i] = fv + gv;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { s.x[i] = np_[i]; s.x[3 + i] = nv[i]; }
+    // M = F P, one column per iteration
+#pragma unroll 1
+    for (int c = 0; c < 9; ++c) {
+        float pp[3], pv[3], pb[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { pp[j] = s.at(j, c); pv[j] = s.at(3 + j, c); pb[j] = s.at(6 + j, c); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float mp = pp[i], mv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { mp += A[i][j] * pv[j]; mv += R[i][j] * pv[j]; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { mp += B[i][j] * pb[j]; mv += A[i][j] * pb[j]; }
+            s.at(i, c) = mp;
+            s.at(3 + i, c) = mv;
+        }
+    }
+    // N = M F^T, one row per iteration
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        float mp3[3], mv[3], mb[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { mp3[j] = s.at(r, j); mv[j] = s.at(r, 3 + j); mb[j] = s.at(r, 6 + j); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float np2 = mp3[i], nv2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { np2 += mv[j] * A[i][j]; nv2 += mv[j] * R[i][j]; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { np2 += mb[j] * B[i][j]; nv2 += mb[j] * A[i][j]; }
+            s.at(r, i) = np2;
+            s.at(r, 3 + i) = nv2;
+        }
+    }
+    // + G Q G^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float bb = 0.f, ba = 0.f, ab = 0.f, aa = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                bb += (B[i][k] * acc_var[k]) * B[j][k];
+                ba += (B[i][k] * acc_var[k]) * A[j][k];
+                ab += (A[i][k] * acc_var[k]) * B[j][k];
+                aa += (A[i][k] * acc_var[k]) * A[j][k];
+            }
+            s.at(i, j) += bb; s.at(i, 3 + j) += ba; s.at(3 + i, j) += ab; s.at(3 + i, 3 + j) += aa;
+        }
+}
+
+template <int LO, int STRIDE>
+__device__ __forceinline__ void pv_correct(PVShared<STRIDE>& s, const float z[3], const float rvar[3]) {
+    // rows H of the OLD covariance (also S = P[H,H] + diag(rvar))
+    float PH[3][9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) PH[k][j] = s.at(LO + k, j);
+    float S[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) S[i][j] = PH[i][LO + j] + (i == j ? rvar[i] : 0.f);
+    const float c00 = S[1][1] * S[2][2] - S[1][2] * S[2][1];
+    const float c01 = S[1][2] * S[2][0] - S[1][0] * S[2][2];
+    const float c02 = S[1][0] * S[2][1] - S[1][1] * S[2][0];
+    const float det = (S[0][0] * c00 + S[0][1] * c01) + S[0][2] * c02;
+    const float id = 1.0f / det;
+    float Si[3][3];
+    Si[0][0] = c00 * id; Si[1][0] = c01 * id; Si[2][0] = c02 * id;
+    Si[0][1] = (S[0][2] * S[2][1] - S[0][1] * S[2][2]) * id;
+    Si[1][1] = (S[0][0] * S[2][2] - S[0][2] * S[2][0]) * id;
+    Si[2][1] = (S[0][1] * S[2][0] - S[0][0] * S[2][1]) * id;
+    Si[0][2] = (S[0][1] * S[1][2] - S[0][2] * S[1][1]) * id;
+    Si[1][2] = (S[0][2] * S[1][0] - S[0][0] * S[1][2]) * id;
+    Si[2][2] = (S[0][0] * S[1][1] - S[0][1] * S[1][0]) * id;
+    const float inn[3] = {z[0] - s.x[LO], z[1] - s.x[LO + 1], z[2] - s.x[LO + 2]};
+    // one row of K, x and P per iteration: row i of K needs only row i of the old P, read before the row is overwritten
+    float xn[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) xn[i] = s.x[i];
+#pragma unroll 1
+    for (int i = 0; i < 9; ++i) {
+        float row[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) row[j] = s.at(i, j);
+        float K[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) K[j] = (row[LO] * Si[0][j] + row[LO + 1] * Si[1][j]) + row[LO + 2] * Si[2][j];
+        const float dx = (K[0] * inn[0] + K[1] * inn[1]) + K[2] * inn[2];
+#pragma unroll
+        for (int ii = 0; ii < 9; ++ii) xn[ii] = (ii == i) ? xn[ii] + dx : xn[ii];      // select chain: no dynamic register index
+        float w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = ((i == LO + k) ? 1.0f : 0.0f) - K[k];
+        const bool inH = (i >= LO) && (i < LO + 3);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float acc3 = (w[0] * PH[0][j] + w[1] * PH[1][j]) + w[2] * PH[2][j];
+            s.at(i, j) = inH ? acc3 : (row[j] + acc3);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s.x[i] = xn[i];
+}
+
 // ------------------------------------------------------------------------------------------------ K2: attitude EKF
 struct EKF4 {
     double q[4];        // wxyz

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cmath>
 #include "internal.h"
+#include "bulk_copy.cuh"
 
 namespace ozl {
 
@@ -56,22 +57,6 @@ __device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const 
     *plane4_ptr(pl, 4, i) = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
     *plane4_ptr(pl, 5, i) = make_float4(e.inv_m, e.ixx, e.iyy, e.izz);
     *plane4_ptr(pl, 6, i) = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
-}
-
-// TMA 1-D bulk copy shared -> global (SASS: UBLKCP).  Used to write the block's contiguous [BLOCK,13] observation
-// tile with one instruction instead of a per-thread copy loop.
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
 }
 
 // Episode statistics (K6) + step-counter retirement at the end of a block.
@@ -238,31 +223,6 @@ constexpr int kTmaActOff = kTmaStateBytes;                        // actions  [1
 constexpr int kTmaProgOff = kTmaActOff + kTile * 16;              // progress [128] int64    1024 B
 constexpr int kTmaRstOff = kTmaProgOff + kTile * 8;               // reset    [128] int64    1024 B
 constexpr int kTmaStageBytes = kTmaRstOff + kTile * 8;            // 19456
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 #ifndef OZL_TMA_MINB
 #define OZL_TMA_MINB 5
