@@ -161,5 +161,26 @@ class EKFLeeLanded(_VehicleTargetTask):
         return int(self.sim.metrics()[2].item())
 
     @property
+    def resets(self):
+        """The reference's `self.epi` (ekf_lee_landed.py:316): number of env resets applied, the initial one included."""
+        return int(self.sim.metrics()[15].item())
+
+    def write_metrics(self, log_dir):
+        """The two files an EKFLeeLanded evaluation run leaves behind (ekf_lee_landed.py:319-331), from the device-side episode
+        statistics (one host read when called, instead of two file writes inside every step):
+          <log_dir>/metrics/<pomdp>_<prob>_ep_count.txt   resets applied so far (`self.epi`)
+          <log_dir>/metrics/<pomdp>_<prob>.txt            episodes that ended after the vehicle was reached (`self.Landoa`)"""
+        import os
+        env = self.cfg["env"]
+        tag = f"{env.get('POMDP', 'none')}_{float(env.get('pomdp_prob', 0.0))}"
+        os.makedirs(os.path.join(log_dir, "metrics"), exist_ok=True)
+        m = self.sim.metrics().cpu()
+        with open(os.path.join(log_dir, "metrics", f"{tag}_ep_count.txt"), "w") as f:
+            f.write(str(int(m[15])))
+        with open(os.path.join(log_dir, "metrics", f"{tag}.txt"), "w") as f:
+            f.write(str(int(m[2])))
+        return int(m[2]), int(m[15])
+
+    @property
     def episodes(self):
         return int(self.sim.metrics()[9].item())

@@ -450,3 +450,23 @@ def test_graphed_rollout_collection_runs_and_tracks_step_counter(tmp_path):
     save_actor(actor, str(tmp_path / "ckpt"))
     a2 = load_actor(RecurrentActor(), str(tmp_path / "ckpt"), map_location="cpu")
     assert all(torch.equal(p.cpu(), q) for p, q in zip(actor.state_dict().values(), a2.state_dict().values()))
+
+
+def test_ekf_lee_experiment_protocol_writes_reference_metric_files(tmp_path):
+    """EKFLeeExperiments.sh protocol (benchmarks/ekf_lee_experiments.py): one run per sensor-fault setting leaves
+    metrics/<pomdp>_<prob>.txt and metrics/<pomdp>_<prob>_ep_count.txt (ekf_lee_landed.py:319-331) with plain integers that
+    agree with the device-side episode statistics."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "ekf_lee_experiments", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks", "ekf_lee_experiments.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert len(mod.SWEEP) == 10 and ("flicker", 0.0) in mod.SWEEP and ("flickering_and_random_noise", 0.25) in mod.SWEEP
+    for pomdp, prob in [("flicker", 0.3), ("random_noise", 0.15)]:
+        line = mod.run_setting(pomdp, prob, 64, 160, str(tmp_path), False, ConvergenceTime=10, maxEpisodeLength=60)
+        land = int((tmp_path / "metrics" / f"{pomdp}_{prob}.txt").read_text())
+        eps = int((tmp_path / "metrics" / f"{pomdp}_{prob}_ep_count.txt").read_text())
+        assert land == line["landings"] and eps == line["resets"]
+        assert eps >= 64 + line["episodes_finished"] - 64          # every finished episode is re-spawned at most one step later
+        assert 0 <= land <= line["episodes_finished"] and line["episodes_finished"] >= 64      # maxEpisodeLength 60 < 160 steps
