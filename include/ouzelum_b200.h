@@ -115,6 +115,20 @@ int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t
 int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
                   int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
 
+/* ozl_step_host + cudaStreamSynchronize in one call, arguments in a block the caller can fill once: the per-step cost on the
+ * host side is one foreign call.  When it returns 0 the host buffers hold this step's results. */
+typedef struct ozl_host_io {
+    const float* actions_host;  /* [N,4] pinned */
+    float* obs_host;            /* [N,13] pinned */
+    float* rew_host;            /* [N] pinned */
+    uint8_t* done_host;         /* [N] pinned */
+    int64_t* reset;             /* [N] device */
+    int64_t* progress;          /* [N] device */
+    uint8_t* timeout;           /* [N] device or NULL */
+    float* ep_ret;              /* [N] device or NULL */
+} ozl_host_io;
+int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream);
+
 /* Same step with the target supplied by the caller every step instead of being re-sampled in-kernel: the landing
  * family, whose target rides on a ground vehicle (tasks/landing.py:373-374, lando.py, landed.py).  target3 [N,3] f32. */
 int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,

@@ -53,6 +53,12 @@ class OzlCfg(C.Structure):
         return self
 
 
+class OzlHostIo(C.Structure):
+    """Mirror of `struct ozl_host_io` (include/ouzelum_b200.h)."""
+    _fields_ = [("actions_host", C.c_void_p), ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("done_host", C.c_void_p),
+                ("reset", C.c_void_p), ("progress", C.c_void_p), ("timeout", C.c_void_p), ("ep_ret", C.c_void_p)]
+
+
 class OzlPvArgs(C.Structure):
     """Mirror of `struct ozl_pv_args` (include/ouzelum_b200.h)."""
     _fields_ = [
@@ -113,6 +119,7 @@ _SIGS = {
     "ozl_reset_all": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_step": (C.c_int, [_P] * 9),
     "ozl_step_host": (C.c_int, [_P] * 10),
+    "ozl_step_host_sync": (C.c_int, [_P, _P, _P]),
     "ozl_step_tracking": (C.c_int, [_P] * 10),
     "ozl_step_wrench": (C.c_int, [_P] * 10),
     "ozl_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

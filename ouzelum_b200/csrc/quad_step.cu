@@ -816,6 +816,14 @@ extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs
                        "ozl_step_host", done_host, host_bulk);
 }
 
+extern "C" int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream) {
+    if (!io) return set_error("ozl_step_host_sync: io is NULL");
+    if (ozl_step_host(env, io->actions_host, io->obs_host, io->rew_host, io->done_host, io->reset, io->progress, io->timeout,
+                      io->ep_ret, stream))
+        return 1;
+    return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+
 extern "C" int ozl_step_tracking(ozl_env* env, const float* actions, const float* target3, float* obs, float* rew,
                                  int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
     if (!target3) return set_error("ozl_step_tracking: target3 is NULL");
