@@ -77,7 +77,7 @@ def config3():
     alg = 1372
     return {"config": 3, "workload": "x500 + DR + sensor noise sigma 0.15 + EKF (f64) + PV filter (full 9x9) + Lee controller, 65536 envs",
             "env_steps_per_sec": n * steps / dt, "us_per_step": dt / steps * 1e6, "alg_bytes_per_env_step": alg,
-            "achieved_GBps_alg": alg * n * steps / dt / 1e9, "launches_per_step": 3,
+            "achieved_GBps_alg": alg * n * steps / dt / 1e9, "launches_per_step": 1,
             "per_env_sensor_triggers_env_steps_per_sec": n * steps / dt2,
             "landings": env.landings, "episodes": env.episodes}
 

@@ -271,6 +271,16 @@ typedef struct ozl_ekf_lee_args {
 } ozl_ekf_lee_args;
 int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* args, void* stream);
 
+/* The WHOLE EKFLeeLanded control step in one launch: vehicle carrying the target (ozl_husky_step), estimator + controller
+ * (ozl_ekf_lee_step) and the physics / observation / reward / reset step with that wrench and target (ozl_step_wrench),
+ * per env in one thread, state read once.  Replaces VecTask.step for isaacgymenvs/tasks/ekf_lee_landed.py
+ * (pre_physics_step :308-530, post_physics_step :620-665).  `husky` follows the env's device step counter (its `step` /
+ * `step_ptr` fields are ignored); `reset` must be the buffer named in `args->reset` (and `husky->reset` if set).
+ * Float results agree with the three-launch sequence to rounding (this translation unit keeps FMA contraction on). */
+struct ozl_husky_args;
+int ozl_ekf_lee_landed_step(ozl_env* env, const ozl_ekf_lee_args* args, const struct ozl_husky_args* husky, float* obs,
+                            float* rew, int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
+
 /* Device address of the handle's step counter, for kernels that must follow it without a host round trip.
  * The counter is a 16-byte record of two uint64 words: word0 = base | (shift << 58), word1 = units, and
  *     step = (word0 & (2^58 - 1)) + (word1 >> (word0 >> 58)).

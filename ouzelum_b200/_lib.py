@@ -143,6 +143,7 @@ _SIGS = {
     "ozl_waypoint_command": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "ozl_apply_resets": (C.c_int, [_P, _P, _P]),
     "ozl_ekf_lee_step": (C.c_int, [_P, C.POINTER(OzlEkfLeeArgs), _P]),
+    "ozl_ekf_lee_landed_step": (C.c_int, [_P] * 10),
     "ozl_step_counter_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int32, _P, _P, _P]),

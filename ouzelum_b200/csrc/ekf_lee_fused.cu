@@ -8,6 +8,8 @@
 //   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
 #include "internal.h"
 #include "bulk_copy.cuh"
+#include "quad_io.cuh"
+#include "targets.cuh"
 #include "filters.cuh"
 #include "glue.cuh"
 #include "lee_control.cuh"
@@ -49,8 +51,18 @@ constexpr int kEkfBlock = OZL_EKF_BLOCK;
 //   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared)
 //   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
 //   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
+// WITH_STEP = true is the WHOLE EKFLeeLanded control step in one launch (ozl_ekf_lee_landed_step): the ground vehicle that
+// carries the target runs first (targets.cuh), and after the controller the same thread applies its wrench to its env --
+// env_step(ACT_WRENCH) with the vehicle's target, sensor-fault epilogue on the observation, stores, episode statistics and
+// the step-counter retirement of quad_step_kernel (quad_io.cuh).  The observation tile reuses the covariance tile's shared
+// memory once the bulk drain has read it.  Replaces three launches (husky_step, ekf_lee_fused, quad_step) and their re-reads.
+struct StepIo {
+    float* obs; float* rew; int64_t* reset; int64_t* progress; uint8_t* timeout; float* ep_ret;
+};
+
+template <bool WITH_STEP>
 __global__ void __launch_bounds__(kEkfBlock, OZL_EKF_MINB)
-ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma) {
+ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma, const HuskyArgs h, const StepIo io) {
     __shared__ __align__(128) float s_P[81 * kEkfBlock];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint64_t s_step;
@@ -80,8 +92,11 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     const uint32_t genv = c.env_id_base + (uint32_t)i;
     // live across the block barrier that precedes the drain of the covariance tile: controller inputs
     float q[4], w[3], est_p[3], est_v[3], cmd[4];
+    float tgt[3] = {0.f, 0.f, 0.f};
+    bool rst = false;
     if (valid) {
-        const bool rst = a.reset[i] != 0;
+        rst = a.reset[i] != 0;
+        if (WITH_STEP) husky_step_env(h, i, step, tgt);     // landing target for this step (landing.py:373-374)
         // ---- true root state (post reset_idx)
         float p[3], v[3];
         if (rst) {
@@ -149,7 +164,9 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         }
         // (the TMA drain of the tile is issued below, after the block barrier, and overlaps the controller)
         // ---- waypoint + controller (:458-529)
-        const float t[3] = {a.target[i * 3], a.target[i * 3 + 1], a.target[i * 3 + 2]};
+        float t[3];
+        if (WITH_STEP) { t[0] = tgt[0]; t[1] = tgt[1]; t[2] = tgt[2]; }
+        else { t[0] = a.target[i * 3]; t[1] = a.target[i * 3 + 1]; t[2] = a.target[i * 3 + 2]; }
         float wp[3] = {a.waypoint[i * 3], a.waypoint[i * 3 + 1], a.waypoint[i * 3 + 2]};
         waypoint_update(p, t, wp, warm);
         for (int j = 0; j < 3; ++j) a.waypoint[i * 3 + j] = wp[j];
@@ -172,8 +189,8 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             bulk_commit();
         }
     }
+    float4 wr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        float4 wr;
         if (warm) {
             wr = make_float4(a.hover, 0.f, 0.f, 0.f);                                     // :526-528
         } else {
@@ -184,13 +201,53 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         a.wrench[i] = wr;
     }
     if (use_tma && tid == 0) bulk_wait_read_all();      // the tile must stay alive until the bulk stores have read it
+    if (!WITH_STEP) return;
+
+    // ---- the env step itself (quad_step_kernel's body, wrench actuation, target from the vehicle)
+    StepOut o;
+    o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
+    o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
+    float* s_obs = s_P;                                  // reused: [kEkfBlock][13] observation tile
+    __syncthreads();                                     // every thread is done with its covariance column, drain has read the tile
+    if (valid) {
+        Loaded L;
+        load_env(pl, i, L);
+        const int64_t prog = io.progress[i];
+        Env e;
+        unpack(L, e);
+        const float act[4] = {wr.x, wr.y, wr.z, wr.w};
+        env_step(e, act, prog, rst, genv, step, c, o, ACT_WRENCH, tgt);
+        obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
+        store_dynamic(pl, i, e);
+        store_static(pl, i, e);
+        io.rew[i] = o.rew;
+        io.reset[i] = o.reset ? 1 : 0;
+        io.progress[i] = o.prog;
+        if (io.timeout) io.timeout[i] = o.timeout ? 1 : 0;
+        if (io.ep_ret) io.ep_ret[i] = o.ep_ret_done;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) s_obs[tid * 13 + j] = o.obs[j];
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    {
+        float* dst = io.obs + base * 13;
+        const int nflt = n_here * 13;
+        if ((nflt & 3) == 0) {
+            if (tid == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
+        } else {
+            for (int k = tid; k < nflt; k += kEkfBlock) dst[k] = s_obs[k];
+        }
+    }
+    block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, 1ull + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
+    if (tid == 0) bulk_wait_read_all();
 }
 
 }  // namespace ozl
 
 using namespace ozl;
 
-extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* stream) {
+static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_husky_args* husky, const StepIo io, void* stream) {
     if (!env || !in) return set_error("ozl_ekf_lee_step: NULL argument");
     if (!in->ekf_q4xN || !in->ekf_P16xN || !in->pv_x9xN || !in->pv_P81xN || !in->prev_linvel3 || !in->waypoint3 || !in->target3 ||
         !in->reset || !in->wrench4 || !in->gains16)
@@ -217,8 +274,32 @@ extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* 
     for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
     // TMA path: every [k][N] plane slice of a block must start on a 16-byte boundary and be a multiple of 16 bytes long
     const int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);
-    ekf_lee_fused_kernel<<<(unsigned)((a.n + kEkfBlock - 1) / kEkfBlock), kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma);
+    const unsigned grid = (unsigned)((a.n + kEkfBlock - 1) / kEkfBlock);
+    if (husky) {
+        HuskyArgs h;
+        if (ozl_fill_husky_args(husky, h, "ozl_ekf_lee_landed_step")) return 1;
+        if (!h.tables) return set_error("ozl_ekf_lee_landed_step: tables204x2 is NULL");
+        if (h.n != a.n) return set_error("ozl_ekf_lee_landed_step: vehicle count %lld != env count %lld", (long long)h.n, (long long)a.n);
+        if (!io.obs || !io.rew || !io.reset || !io.progress) return set_error("ozl_ekf_lee_landed_step: NULL buffer");
+        if ((uintptr_t)io.obs & 15) return set_error("ozl_ekf_lee_landed_step: obs must be 16-byte aligned");
+        if (io.reset != a.reset || (h.reset && h.reset != a.reset))
+            return set_error("ozl_ekf_lee_landed_step: the estimator, the vehicle and the step must see the same reset buffer");
+        ekf_lee_fused_kernel<true><<<grid, kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma, h, io);
+    } else {
+        ekf_lee_fused_kernel<false><<<grid, kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma, HuskyArgs{}, io);
+    }
     return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
+}
+
+extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* stream) {
+    return launch_ekf_lee(env, in, nullptr, StepIo{}, stream);
+}
+
+extern "C" int ozl_ekf_lee_landed_step(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_husky_args* husky, float* obs,
+                                       float* rew, int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret,
+                                       void* stream) {
+    if (!husky) return set_error("ozl_ekf_lee_landed_step: husky args are NULL");
+    return launch_ekf_lee(env, in, husky, StepIo{obs, rew, reset, progress, timeout, ep_ret}, stream);
 }
 
 extern "C" int ozl_step_counter_ptr(ozl_env* env, const uint64_t** out) {

@@ -42,6 +42,7 @@ class EKFLeeLanded(_VehicleTargetTask):
         self._pomdp_prob = float(env.get("pomdp_prob", 0.0))
         self.per_env_triggers = bool(env.get("perEnvSensorTriggers", False))
         self.fused = bool(env.get("fusedEstimator", True))      # one kernel for the whole estimator + controller chain
+        self.fused_step = bool(env.get("fusedStep", True))      # ... and the vehicle + physics step in the same launch
         super().__init__(cfg, *a, **k)
 
     def _native_cfg(self):
@@ -112,9 +113,22 @@ class EKFLeeLanded(_VehicleTargetTask):
         return self._launch_chain()
 
     def _launch_fused(self):
-        """vehicle kernel -> fused estimator+controller kernel -> step kernel: three launches, no host-changing arguments."""
+        """fusedStep: the whole control step in one launch; otherwise vehicle kernel -> fused estimator+controller kernel ->
+        step kernel (three launches).  No host-changing arguments either way (CUDA-graph capturable)."""
         import ctypes as C
         self._fa.reset = self.reset_buf.data_ptr()
+        if self.fused_step:
+            # ONE launch: vehicle -> estimator + controller -> physics / observation / reward / reset (ozl_ekf_lee_landed_step)
+            from .._lib import ptr
+            ha = self.husky._a
+            ha.reset = self.reset_buf.data_ptr()
+            check(lib.ozl_ekf_lee_landed_step(self.sim._h, C.byref(self._fa), C.byref(ha), self.obs_buf.data_ptr(),
+                                              self.rew_buf.data_ptr(), self.reset_buf.data_ptr(), self.progress_buf.data_ptr(),
+                                              self._timeout_u8.data_ptr(), self.episode_return_buf.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+            self._target = self.husky.target
+            self.sim_step_count += 1
+            return
         self._target = self.husky.step(self.reset_buf)
         check(lib.ozl_ekf_lee_step(self.sim._h, C.byref(self._fa), torch.cuda.current_stream().cuda_stream))
         self.sim.step_wrench(self._wrench, self._target, self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf,

@@ -269,10 +269,11 @@ def test_step_host_zero_copy_matches_device_step():
         e2.step_host(torch.zeros(n, 4))          # not pinned
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_ekf_lee_fused_kernel_equals_kernel_chain(graph):
+@pytest.mark.parametrize("graph,fused_step", [(False, False), (True, False), (False, True), (True, True)])
+def test_ekf_lee_fused_kernel_equals_kernel_chain(graph, fused_step):
     """The single fused estimator+controller kernel (ozl_ekf_lee_step) against the 9-launch chain of stand-alone kernels
-    (each of which is tested against the oracle).  Both are built from the same device functions, but with FMA contraction on
+    (each of which is tested against the oracle); with `fused_step` the vehicle and the physics step ride in the same launch
+    (ozl_ekf_lee_landed_step).  All are built from the same device functions, but with FMA contraction on
     the compiler may fuse differently in the two contexts, so the comparison is step-by-step from IDENTICAL state (the
     chain env's state is copied into the fused env before every step) with float tolerances; integer outputs must agree."""
     import ouzelum_b200
@@ -280,7 +281,7 @@ def test_ekf_lee_fused_kernel_equals_kernel_chain(graph):
     mk = lambda fused: ouzelum_b200.make(seed=6, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
                                          cfg=ouzelum_b200.task_config("EKFLeeLanded", n, seed=6, ConvergenceTime=7, POMDP="flickering_and_random_noise",
                                                                       pomdp_prob=0.1, maxEpisodeLength=30, fusedEstimator=fused,
-                                                                      useCudaGraph=(graph and fused)))
+                                                                      fusedStep=fused_step, useCudaGraph=(graph and fused)))
     e1, e2 = mk(False), mk(True)
     a = torch.zeros(n, 4, device=DEV)
     flips = 0
