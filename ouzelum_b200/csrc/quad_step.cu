@@ -157,10 +157,7 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
     __shared__ double s_m[kTile / 32][11];
     const int tid = threadIdx.x;
     __shared__ uint64_t s_step;
-    if (tid == 0) { s_step = read_step(pl.ctrl); mbar_init(&s_bar, 1); }
-    __syncthreads();
-    const uint64_t step = s_step;
-    const bool blackout = flicker_blackout(step, c);
+    __shared__ long long s_next;
 
     auto issue = [&](int64_t tile) {            // thread 0 only
         mbar_expect_tx(&s_bar, kTmaStageBytes);
@@ -171,13 +168,18 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
     };
     // dynamic tile scheduler: the first tile of a CTA is its block index, further tiles come from a device counter (ctrl[4]);
     // thread 0 requests the index one iteration ahead so the atomic's round trip never sits on the critical path
-    __shared__ long long s_next;
+    // Prologue order: the first tile's loads go out before anything else, the step index (one L2 round trip) is read behind them.
     int64_t tile = blockIdx.x;
     long long nxt = 0;
     if (tid == 0) {
+        mbar_init(&s_bar, 1);
         if (tile < full_tiles) issue(tile);
         nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
+        s_step = read_step(pl.ctrl);
     }
+    __syncthreads();
+    const uint64_t step = s_step;
+    const bool blackout = flicker_blackout(step, c);
 
     // metric accumulators over all tiles of this CTA (per-thread counts packed 16 bits each; the host keeps the average number of
     // tiles per CTA below 8192, and the dynamic scheduler spreads them evenly)
