@@ -148,3 +148,23 @@ def test_recurrent_actor_cell_equals_nn_lstm():
         _, s2 = a.lstm(a.network(obs).unsqueeze(0), (keep * st[0], keep * st[1]))
     assert act.shape == (n, 4) and logp.shape == (n,)
     assert (s1[0] - s2[0]).abs().max() < 1e-5 and (s1[1] - s2[1]).abs().max() < 1e-5
+
+
+def test_c_abi_argument_errors_need_no_gpu(lib):
+    """Argument validation happens before any CUDA call: non-zero return + a message in ozl_last_error()."""
+    L = lib.lib
+    msg = lambda: L.ozl_last_error().decode()
+    assert L.ozl_step(None, None, None, None, None, None, None, None, None) != 0 and "env is NULL" in msg()
+    assert L.ozl_step_host_sync(None, None, None) != 0 and "io is NULL" in msg()
+    io = lib.OzlHostIo()
+    assert L.ozl_step_host_sync(None, ctypes.byref(io), None) != 0 and "done_host is NULL" in msg()
+    assert L.ozl_ekf_lee_landed_step(None, None, None, None, None, None, None, None, None, None) != 0 and "husky args are NULL" in msg()
+    assert L.ozl_ekf_lee_step(None, None, None) != 0 and "NULL argument" in msg()
+    assert L.ozl_rollout(None, 4, None, None, None, None, None) != 0 and "env is NULL" in msg()
+    out = ctypes.c_uint64()
+    assert L.ozl_get_step_count(None, ctypes.byref(out), None) != 0 and "env is NULL" in msg()
+    assert L.ozl_cfg_default(None, 16) != 0 and "cfg is NULL" in msg()
+    bad = lib.default_cfg(16)
+    bad.abi_version = 999
+    h = ctypes.c_void_p()
+    assert L.ozl_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0 and "abi_version" in msg()
