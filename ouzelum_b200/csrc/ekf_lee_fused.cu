@@ -43,6 +43,7 @@ struct EkfLeeArgs {
 #define OZL_EKF_MINB 4
 #endif
 constexpr int kEkfBlock = OZL_EKF_BLOCK;
+static_assert(kEkfBlock == kTile, "the one-launch step retires one step-counter work unit per 128-env block (step_counter.cuh)");
 
 // Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA):
 //   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by thread 0 with 81 TMA

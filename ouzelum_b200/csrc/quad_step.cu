@@ -708,7 +708,6 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         !(((uintptr_t)progress | (uintptr_t)reset) & 15)) {
         // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
         unsigned grid = (unsigned)(full_tiles < resident ? full_tiles : resident);
-        { static const char* eg = getenv("OZL_TMA_GRID"); if (eg && atoi(eg) > 0 && (int64_t)atoi(eg) <= full_tiles) grid = (unsigned)atoi(eg); }   // tuning aid
         while ((full_tiles + grid - 1) / grid > 8192) grid *= 2;     // 16-bit packed metric counters: keep tiles per CTA far below 65535
         quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
                                                       ep_ret, full_tiles);
@@ -732,10 +731,9 @@ extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* r
 extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
                              int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
     if (!done_host) return set_error("ozl_step_host: done_host is NULL");
-    // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store
-    static const int host_bulk = getenv("OZL_HOST_BULK") ? atoi(getenv("OZL_HOST_BULK")) : 0;
+    // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store (measured equal)
     return launch_step(env, actions_host, nullptr, ACT_ROTORS, obs_host, rew_host, reset, progress, timeout, ep_ret, stream,
-                       "ozl_step_host", done_host, host_bulk);
+                       "ozl_step_host", done_host, 0);
 }
 
 extern "C" int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream) {

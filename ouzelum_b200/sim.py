@@ -14,7 +14,8 @@ from ._lib import check, lib, ptr
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of torch's current stream on the current device (the fast path of torch.cuda.current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 class QuadSim:

@@ -29,6 +29,8 @@ class Env:
             raise RuntimeError(f"sim_device={sim_device!r}: ouzelum_b200 has no CPU pipeline (sm_100a CUDA only)")
         self.device = "cuda:" + str(self.device_id)
         self.rl_device = rl_device
+        self._tdev = torch.device(self.device)
+        self._rl_on_sim_device = torch.device(rl_device) == self._tdev
         self.headless = headless
         self.graphics_device_id = -1 if headless else graphics_device_id
 
@@ -119,7 +121,7 @@ class VecTask(Env):
     def step(self, actions: torch.Tensor) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, Dict[str, Any]]:
         """vec_task.py:313-359.  Action clamp, pre/post physics, reward, reset flags, time-outs and the
         observation clamp all happen inside the one kernel `_fused_step` launches."""
-        if actions.dtype != torch.float32 or not actions.is_contiguous() or str(actions.device) != self.device:
+        if actions.dtype != torch.float32 or actions.device != self._tdev or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if _NVTX:                                   # OUZELUM_B200_NVTX=1: one NVTX range per env step (nsys / ncu --nvtx)
             torch.cuda.nvtx.range_push(f"{type(self).__name__}.step")
@@ -127,6 +129,12 @@ class VecTask(Env):
             torch.cuda.nvtx.range_pop()
         else:
             self._fused_step(actions)
+        if self._rl_on_sim_device:                  # the usual case: no `.to()` round trips through the dispatcher
+            self.extras["time_outs"] = self.timeout_buf
+            self.obs_dict["obs"] = self.obs_buf
+            if self.num_states > 0:
+                self.obs_dict["states"] = self.get_state()
+            return self.obs_dict, self.rew_buf, self.reset_buf, self.extras
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
         if self.num_states > 0:
