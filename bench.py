@@ -435,28 +435,57 @@ def run_ours(args):
         ab = [torch.rand(nb, 4, device=dev) * 2 - 1 for _ in range(2)]
         for k in range(10):
             simb.step(ab[k & 1], ob, rb, rsb, pb, tb, eb)
-        torch.cuda.synchronize()
         reps_b = 50
+        gb = graph_of(lambda k: simb.step(ab[k & 1], ob, rb, rsb, pb, tb, eb), reps_b)     # launches back to back, no host gaps
+        gb.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks.region(True)
         e0.record()
-        for k in range(reps_b):
-            simb.step(ab[k & 1], ob, rb, rsb, pb, tb, eb)
+        gb.replay()
         e1.record()
         torch.cuda.synchronize()
         clocks.region(False)
         per_launch_s = e0.elapsed_time(e1) * 1e-3 / reps_b
+        del gb
         ach = ALG_BYTES_PER_ENV_STEP * nb / per_launch_s / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                     "kernel": "quad_step_tma_kernel (persistent, TMA-pipelined; the same step as quad_step_kernel<128> which serves N < ~450k)", "n_envs": nb, "launch_us": per_launch_s * 1e6,
                     "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "peak_source": peak_src,
-                    "l2": "inputs (311 MB/launch) exceed the 126 MB L2; no flush",
+                    "l2": "inputs (311 MB/launch) exceed the 126 MB L2; no flush; 50 launches replayed from a CUDA graph, one event pair",
                     "env_steps_per_sec_at_this_size": nb / per_launch_s}
+        del simb, ob, rb, rsb, pb, tb, eb, ab
+        # the same measurement over the shard sizes of BASELINE config 4 (1 Mi envs over 8 / 4 / 2 / 1 GPUs) and 4 Mi: how the
+        # step approaches the HBM roofline as a launch grows (<= 262144 envs fit the 126 MB L2 when replayed on one buffer set)
+        sweep = []
+        if not args.roofline_only:
+            for ns in (131072, 262144, 524288, 4194304):
+                sm_ = QuadSim(_lib.default_cfg(ns, seed=args.seed, **task_cfg_kwargs()), dev)
+                o_, r_ = torch.zeros(ns, 13, device=dev), torch.zeros(ns, device=dev)
+                rs_, p_ = torch.ones(ns, dtype=torch.int64, device=dev), torch.zeros(ns, dtype=torch.int64, device=dev)
+                t_, e_ = torch.zeros(ns, dtype=torch.uint8, device=dev), torch.zeros(ns, device=dev)
+                a_ = torch.rand(ns, 4, device=dev) * 2 - 1
+                for _ in range(10):
+                    sm_.step(a_, o_, r_, rs_, p_, t_, e_)
+                reps_s = 40
+                gs_ = graph_of(lambda k: sm_.step(a_, o_, r_, rs_, p_, t_, e_), reps_s)
+                gs_.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gs_.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / reps_s
+                del gs_
+                sweep.append({"n_envs": ns, "launch_us": us, "frac": ALG_BYTES_PER_ENV_STEP * ns / (us * 1e-6) / 1e9 / peak,
+                              "l2": "fits L2 (warm)" if ns * 297 < 120e6 else "exceeds L2"})
+                del sm_, o_, r_, rs_, p_, t_, e_, a_
+        roofline["sweep"] = sweep
         ach_wl = ALG_BYTES_PER_ENV_STEP * n / (rot_ms * 1e-3 / K) / 1e9
         roofline_wl = {"bound": "launch/latency (4.9 MB per launch, one partial wave)", "achieved": ach_wl, "peak": peak,
                        "unit": "GB/s", "frac": ach_wl / peak, "n_envs": n, "launch_us": rot_ms * 1e3 / K}
-        del simb
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None

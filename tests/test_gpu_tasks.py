@@ -471,3 +471,41 @@ def test_ekf_lee_experiment_protocol_writes_reference_metric_files(tmp_path):
         assert land == line["landings"] and eps == line["resets"]
         assert eps >= 64 + line["episodes_finished"] - 64          # every finished episode is re-spawned at most one step later
         assert 0 <= land <= line["episodes_finished"] and line["episodes_finished"] >= 64      # maxEpisodeLength 60 < 160 steps
+
+
+@pytest.mark.parametrize("n", [1000, 4096])
+def test_ekf_lee_one_launch_step_tma_path_matches_three_launches(n):
+    """N % 4 == 0 takes the TMA-staged covariance tile (n = 1000: 7 full CTAs + a 104-env partial tile).  The one-launch step
+    (vehicle + estimator + controller + physics) against vehicle / estimator / step as three launches, from identical state."""
+    import ouzelum_b200
+    mk = lambda one: ouzelum_b200.make(seed=11, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                       cfg=ouzelum_b200.task_config("EKFLeeLanded", n, seed=11, ConvergenceTime=5, POMDP="random_noise",
+                                                                    pomdp_prob=0.15, maxEpisodeLength=40, fusedEstimator=True,
+                                                                    fusedStep=one))
+    e1, e2 = mk(False), mk(True)
+    a = torch.zeros(n, 4, device=DEV)
+    flips = 0
+    for t in range(45):
+        st = e1.sim.get_state()
+        e2.sim.set_state(root=st["root"], thrust=st["thrust"], target=st["target"], ep_ret=st["ep_ret"])
+        e2.ekf._q.copy_(e1.ekf._q), e2.ekf._P.copy_(e1.ekf._P)
+        e2.pvfilters._x.copy_(e1.pvfilters._x), e2.pvfilters._P.copy_(e1.pvfilters._P)
+        e2.prev_root_linvels.copy_(e1.prev_root_linvels), e2.target_waypoints.copy_(e1.target_waypoints)
+        e2.husky.pose.copy_(e1.husky.pose), e2.husky.idx.copy_(e1.husky.idx)
+        e2.reset_buf.copy_(e1.reset_buf), e2.progress_buf.copy_(e1.progress_buf)
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        assert torch.equal(e2.husky.pose, e1.husky.pose) and torch.equal(e2.husky.idx, e1.husky.idx), t     # same vehicle code, same TU
+        assert torch.equal(e2._target, e1._target), t
+        torch.testing.assert_close(e2.ekf._q, e1.ekf._q, rtol=1e-10, atol=1e-12)
+        torch.testing.assert_close(e2.ekf._P, e1.ekf._P, rtol=1e-9, atol=1e-15)
+        sx = float(e1.pvfilters._x.abs().max()) + 1.0
+        torch.testing.assert_close(e2.pvfilters._x, e1.pvfilters._x, rtol=1e-3, atol=1e-4 * sx)
+        if t >= 5:
+            torch.testing.assert_close(e2._wrench, e1._wrench, rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(o2["obs"], o1["obs"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(r2, r1, rtol=1e-4, atol=1e-5)
+        assert torch.equal(e2.progress_buf * (1 - d2), e1.progress_buf * (1 - d1)) or int((d1 != d2).sum()) > 0
+        flips += int((d1 != d2).sum())
+    assert flips <= 2, flips
+    assert e1.sim.step_count == e2.sim.step_count == 45
