@@ -46,6 +46,13 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
                  : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A step kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// made resident while its predecessor on the stream is still draining; griddep_wait() blocks until the predecessor has
+// completed and its memory operations are visible (it returns at once when the launch carries no such dependency), and
+// griddep_launch_dependents() lets the NEXT launch on the stream be staged the same way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

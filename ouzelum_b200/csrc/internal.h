@@ -64,6 +64,7 @@ struct ozl_env {
     int device;
     int sm_count;
     long long tma_min_tiles;    // >= this many whole tiles: use the persistent TMA-pipelined step kernel
+    int use_pdl;                // step launches carry the programmatic-stream-serialization attribute (see launch_step)
     void* arena;                // single cudaMalloc backing all planes
     size_t arena_bytes;
 };

@@ -47,6 +47,8 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
     const int64_t base = env0 + (int64_t)blockIdx.x * BLOCK;
     const int64_t i = base + threadIdx.x;
     const bool valid = i < c.num_envs;
+    griddep_wait();                    // PDL: everything below reads what the previous launch on the stream wrote
+    griddep_launch_dependents();       // ... and the next launch may be staged behind this one from here on
     if (threadIdx.x == 0) s_step = read_step(pl.ctrl);     // one request per block (all of them hit the same L2 slice)
 
     StepOut o;
@@ -171,8 +173,10 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
     // Prologue order: the first tile's loads go out before anything else, the step index (one L2 round trip) is read behind them.
     int64_t tile = blockIdx.x;
     long long nxt = 0;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    griddep_wait();                    // PDL: see quad_step_kernel
+    griddep_launch_dependents();
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
         if (tile < full_tiles) issue(tile);
         nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
         s_step = read_step(pl.ctrl);
@@ -646,6 +650,8 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     e->sm_count = prop.multiProcessorCount;
     {   // switch to the TMA-pipelined kernel once every resident CTA slot gets ~4.75 tiles (measured crossover on B200: generic
         // 21.5 vs 22.3 us at 393216 envs, 31.6 vs 29.4 us at 524288) (override: OZL_TMA_MIN_TILES, 0 = never)
+        const char* pv = getenv("OZL_PDL");
+        e->use_pdl = pv ? atoi(pv) : 1;
         const char* ev = getenv("OZL_TMA_MIN_TILES");
         e->tma_min_tiles = ev ? atoll(ev) : (19ll * prop.multiProcessorCount * OZL_TMA_MINB) / 4;
     }
@@ -693,6 +699,21 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 constexpr int kStepBlock = OZL_STEP_BLOCK;
 static_assert(kStepBlock == kTile, "the step counter retires one work unit per 128-env tile == one block of the generic kernel");
 
+// Step launches go through cudaLaunchKernelEx so that they can carry the programmatic-stream-serialization attribute (PDL):
+// consecutive steps on a stream are strictly dependent, but the NEXT step's blocks can be made resident and parked in
+// griddep_wait() while the current step drains, which takes the launch latency off the critical path of short steps.
+template <typename... KArgs, typename... Args>
+static int launch_pdl(ozl_env* env, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env->use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...) != cudaSuccess;
+}
+
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
                        uint8_t* done_u8 = nullptr, int obs_bulk = 1) {
@@ -709,18 +730,19 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
         unsigned grid = (unsigned)(full_tiles < resident ? full_tiles : resident);
         while ((full_tiles + grid - 1) / grid > 8192) grid *= 2;     // 16-bit packed metric counters: keep tiles per CTA far below 65535
-        quad_step_tma_kernel<<<grid, kTile, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout,
-                                                      ep_ret, full_tiles);
-        if (check_cuda(cudaGetLastError(), "quad_step_tma_kernel")) return 1;
+        if (launch_pdl(env, quad_step_tma_kernel, dim3(grid), dim3(kTile), st, env->dev, env->pl, (const float4*)actions, obs, rew, reset,
+                       progress, timeout, ep_ret, full_tiles))
+            return check_cuda(cudaGetLastError(), "quad_step_tma_kernel");
         if (tail)
             quad_step_kernel<kStepBlock><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress,
                                                                   timeout, ep_ret, nullptr, ACT_ROTORS, nullptr, 1, full_tiles * kTile);
         return check_cuda(cudaGetLastError(), "quad_step_kernel(tail)");
     }
-    quad_step_kernel<kStepBlock><<<blocks_for(n, kStepBlock), kStepBlock, 0, st>>>(
-        env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8,
-        obs_bulk, 0);
-    return check_cuda(cudaGetLastError(), "quad_step_kernel");
+    if (launch_pdl(env, quad_step_kernel<kStepBlock>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev, env->pl,
+                   (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8, obs_bulk,
+                   (int64_t)0))
+        return check_cuda(cudaGetLastError(), "quad_step_kernel");
+    return 0;
 }
 
 extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
