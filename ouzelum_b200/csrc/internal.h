@@ -33,7 +33,7 @@ constexpr int kTileBytes = kTile * (7 * 16 + 8);
 struct Planes {
     char* base;                 // arena
     int64_t plane4, plane2;     // OZL_TILED=0: byte strides of the float4 / float2 planes
-    unsigned long long* ctrl;   // [0..2] step-counter record {base, units, shift} (step_counter.cuh), [4] TMA-kernel tile scheduler, [5] TMA-kernel CTAs done
+    unsigned long long* ctrl;   // [0..2] step-counter record {base, units, shift} (step_counter.cuh), [4] TMA-kernel tile scheduler (monotonic)
     double* metrics;            // kMetricSlots x kMetricStride
 };
 // k = 0..3: d0..d3, k = 4..6: s0..s2

@@ -176,9 +176,16 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
     if (tid == 0) mbar_init(&s_bar, 1);
     griddep_wait();                    // PDL: see quad_step_kernel
     griddep_launch_dependents();
+    // The scheduler counter is MONOTONIC: a launch makes exactly full_tiles requests in total (every CTA makes one per tile it
+    // processes), so the counter stands at a whole multiple of full_tiles between launches and a CTA's first request -- made
+    // before the CTA has contributed its own share -- always returns a value inside the current multiple: no re-arming, hence
+    // no last-CTA election at the tail of the kernel.
+    unsigned long long tile_base = 0;
     if (tid == 0) {
         if (tile < full_tiles) issue(tile);
-        nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
+        const unsigned long long v = atomicAdd(pl.ctrl + 4, 1ull);
+        tile_base = (v / (unsigned long long)full_tiles) * (unsigned long long)full_tiles;
+        nxt = (long long)gridDim.x + (long long)(v - tile_base);
         s_step = read_step(pl.ctrl);
     }
     __syncthreads();
@@ -212,7 +219,7 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         if (tid == 0) {
             if (next < full_tiles) {
                 issue(next);
-                nxt = (long long)gridDim.x + (long long)atomicAdd(pl.ctrl + 4, 1ull);
+                nxt = (long long)gridDim.x + (long long)(atomicAdd(pl.ctrl + 4, 1ull) - tile_base);
             }
         }
 
@@ -274,13 +281,6 @@ quad_step_tma_kernel(const DevCfg c, const Planes pl, const float4* __restrict__
         // step counter: one work unit per tile processed (+ the padding, CTA 0); a ragged tail is retired by the one-block
         // launch of quad_step_kernel that follows on the stream
         retire_units(pl.ctrl, (unsigned long long)m_valid + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
-        // last CTA of this launch re-arms the tile scheduler (once per persistent CTA: off the per-tile path)
-        __threadfence();
-        const unsigned long long t = atomicAdd(pl.ctrl + 5, 1ull);
-        if (t == (unsigned long long)gridDim.x - 1ull) {
-            pl.ctrl[5] = 0ull;
-            pl.ctrl[4] = 0ull;
-        }
     }
 }
 
