@@ -72,10 +72,10 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     const int64_t i = base + tid;
     const bool valid = i < a.n;
     const int n_here = (a.n - base) < kEkfBlock ? (int)(a.n - base) : kEkfBlock;
-    if (tid == 0) {
-        s_step = read_step(pl.ctrl);
-        if (use_tma) mbar_init(&s_bar, 1);
-    }
+    if (tid == 0 && use_tma) mbar_init(&s_bar, 1);
+    griddep_wait();                    // PDL (bulk_copy.cuh): everything below reads what the previous launch wrote
+    griddep_launch_dependents();
+    if (tid == 0) s_step = read_step(pl.ctrl);
     __syncthreads();
     if (use_tma) {
         if (tid == 0) {
@@ -285,11 +285,14 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
         if ((uintptr_t)io.obs & 15) return set_error("ozl_ekf_lee_landed_step: obs must be 16-byte aligned");
         if (io.reset != a.reset || (h.reset && h.reset != a.reset))
             return set_error("ozl_ekf_lee_landed_step: the estimator, the vehicle and the step must see the same reset buffer");
-        ekf_lee_fused_kernel<true><<<grid, kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma, h, io);
+        if (launch_pdl(env, ekf_lee_fused_kernel<true>, dim3(grid), dim3(kEkfBlock), (cudaStream_t)stream, env->dev, env->pl, a, use_tma, h, io))
+            return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
     } else {
-        ekf_lee_fused_kernel<false><<<grid, kEkfBlock, 0, (cudaStream_t)stream>>>(env->dev, env->pl, a, use_tma, HuskyArgs{}, io);
+        if (launch_pdl(env, ekf_lee_fused_kernel<false>, dim3(grid), dim3(kEkfBlock), (cudaStream_t)stream, env->dev, env->pl, a, use_tma,
+                       HuskyArgs{}, io))
+            return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
     }
-    return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
+    return 0;
 }
 
 extern "C" int ozl_ekf_lee_step(ozl_env* env, const ozl_ekf_lee_args* in, void* stream) {

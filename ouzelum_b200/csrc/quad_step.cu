@@ -699,21 +699,6 @@ extern "C" int ozl_reset_all(ozl_env* env, uint64_t seed, void* stream) {
 constexpr int kStepBlock = OZL_STEP_BLOCK;
 static_assert(kStepBlock == kTile, "the step counter retires one work unit per 128-env tile == one block of the generic kernel");
 
-// Step launches go through cudaLaunchKernelEx so that they can carry the programmatic-stream-serialization attribute (PDL):
-// consecutive steps on a stream are strictly dependent, but the NEXT step's blocks can be made resident and parked in
-// griddep_wait() while the current step drains, which takes the launch latency off the critical path of short steps.
-template <typename... KArgs, typename... Args>
-static int launch_pdl(ozl_env* env, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = env->use_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...) != cudaSuccess;
-}
-
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
                        uint8_t* done_u8 = nullptr, int obs_bulk = 1) {
