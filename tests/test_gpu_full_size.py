@@ -82,3 +82,49 @@ def test_sharding_is_pure_slicing_at_scale():
         assert torch.equal(wb[k], torch.cat([b[k] for _, b in shards])), k
     tot = sum(s.metrics().cpu().numpy()[8:16] for s, _ in shards)
     np.testing.assert_array_equal(whole.metrics().cpu().numpy()[8:16], tot)     # what the NCCL all-reduce would produce
+
+
+def test_yaw_180_symmetry_of_the_dynamics_at_scale():
+    """Size-independent physics property, independent of the oracle: rotating the whole world by 180 degrees about z
+    (p, v, omega -> (-x, -y, z); q -> k (x) q = (-y, x, w, -z) in xyzw; target likewise) with the SAME rotor commands gives the
+    rotated trajectory, the same reward and the same termination.  (Gravity and the rotor wrench are z / body-frame quantities.)
+    Holds to float32 rounding -- the rotation matrix of k (x) q equals Rz(pi) R(q) only through |q| = 1 -- so the check is a
+    tolerance over a short horizon, on 1 Mi envs with rotor faults and domain randomisation, before any env can reset."""
+    n, steps = 1 << 20, 12
+    kw = dict(seed=77, fault_mode=1, dr_enable=1, max_episode_length=2000, target_fixed=1, lin_drag=0.05, yaw_km=0.016)
+    a_sim, b_sim = _mk(n, True, **kw), _mk(n, True, **kw)
+    a, b = _bufs(n), _bufs(n)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    zero = torch.zeros(n, 4, device=DEV)
+    for s_, bf in ((a_sim, a), (b_sim, b)):                       # apply the initial reset: identical spawn / fault / DR draws
+        s_.step(zero, bf["obs"], bf["rew"], bf["reset"], bf["progress"], bf["timeout"], bf["ep_ret"])
+    st = a_sim.get_state()
+    root = st["root"].clone()
+    root[:, 7:13] = (torch.rand(n, 6, device=DEV, generator=g) - 0.5) * 0.6           # some motion
+    q = torch.randn(n, 4, device=DEV, generator=g) * 0.15
+    q[:, 3] += 1.0
+    root[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+    root[:, 2] = 3.0                                                                   # high enough not to crash in 12 steps
+    tgt = st["target"].clone()
+    thrust = torch.rand(n, 4, device=DEV, generator=g) * 8.0
+    a_sim.set_state(root=root, thrust=thrust, target=tgt)
+
+    def rot(v3):
+        return torch.stack([-v3[:, 0], -v3[:, 1], v3[:, 2]], 1)
+    rb = root.clone()
+    rb[:, 0:3], rb[:, 7:10], rb[:, 10:13] = rot(root[:, 0:3]), rot(root[:, 7:10]), rot(root[:, 10:13])
+    rb[:, 3:7] = torch.stack([-root[:, 4], root[:, 3], root[:, 6], -root[:, 5]], 1)
+    b_sim.set_state(root=rb, thrust=thrust, target=rot(tgt))
+    for t in range(steps):
+        act = torch.rand(n, 4, device=DEV, generator=g) * 2 - 1
+        a_sim.step(act, a["obs"], a["rew"], a["reset"], a["progress"], a["timeout"], a["ep_ret"])
+        b_sim.step(act, b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+    assert int(a["reset"].sum()) == int(b["reset"].sum()) == 0, "horizon chosen so that no env terminates"
+    ra, rbb = a_sim.get_state()["root"], b_sim.get_state()["root"]
+    torch.testing.assert_close(rot(ra[:, 0:3]), rbb[:, 0:3], rtol=0, atol=2e-5)
+    torch.testing.assert_close(rot(ra[:, 7:10]), rbb[:, 7:10], rtol=0, atol=1e-4)
+    torch.testing.assert_close(rot(ra[:, 10:13]), rbb[:, 10:13], rtol=0, atol=2e-4)
+    qa = torch.stack([-ra[:, 4], ra[:, 3], ra[:, 6], -ra[:, 5]], 1)
+    torch.testing.assert_close(qa, rbb[:, 3:7], rtol=0, atol=1e-5)
+    torch.testing.assert_close(a["rew"], b["rew"], rtol=1e-5, atol=1e-6)
+    assert (ra[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-6                             # the quaternion stays normalised
