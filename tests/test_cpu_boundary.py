@@ -168,3 +168,76 @@ def test_c_abi_argument_errors_need_no_gpu(lib):
     bad.abi_version = 999
     h = ctypes.c_void_p()
     assert L.ozl_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0 and "abi_version" in msg()
+
+
+def test_compat_shims_resolve_the_reference_trainer_imports(lib):
+    """ouzelum_b200.compat (SURVEY 8f rank 1): the module names a reference trainer imports resolve to this package's pieces;
+    the gym stand-in has gym 0.24's Wrapper / ObservationWrapper semantics (what RPO-LSTM/utils.py:4-39 subclasses)."""
+    import importlib
+    import sys
+    import ouzelum_b200
+    from ouzelum_b200 import compat
+    before = {k: sys.modules.get(k) for k in ("gym", "gym.spaces", "isaacgym", "isaacgymenvs", "isaacgymenvs.utils",
+                                              "isaacgymenvs.utils.POMDP", "isaacgymenvs.tasks", "torch.utils.tensorboard")}
+    try:
+        installed = compat.install()
+        assert {"isaacgym", "isaacgymenvs", "gym"} <= set(installed)             # none of them exists in this image
+        import gym
+        import isaacgym  # noqa: F401
+        import isaacgymenvs
+        from isaacgymenvs.utils.POMDP import POMDPWrapper
+        from torch.utils.tensorboard import SummaryWriter
+        assert isaacgymenvs.make is ouzelum_b200.make
+        assert POMDPWrapper is importlib.import_module("ouzelum_b200.pomdp").POMDPWrapper
+        SummaryWriter("x").add_scalar("a", 1.0, 0)
+
+        class Inner:
+            num_envs, action_space = 3, gym.spaces.Box(-1.0, 1.0, (4,))
+
+            def reset(self):
+                return {"obs": "o0"}
+
+            def step(self, a):
+                return {"obs": a}, 1.0, False, {}
+
+        class Extract(gym.ObservationWrapper):
+            def observation(self, obs):
+                return obs["obs"]
+
+        class Count(gym.Wrapper):
+            def __init__(self, env):
+                super().__init__(env)
+                self.n = 0
+
+            def step(self, a):
+                self.n += 1
+                return self.env.step(a)
+        e = Count(Extract(Inner()))
+        assert e.reset() == "o0" and e.step("a1")[0] == "a1" and e.n == 1
+        assert e.num_envs == 3 and isinstance(e.action_space, gym.spaces.Box) and e.action_space.shape == (4,)
+        with pytest.raises(AttributeError):
+            e.no_such_attribute
+        assert compat.install() == []                                            # idempotent: nothing left to install
+    finally:
+        for k, v in before.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/isaacgymenvs/RPO-LSTM/main.py") or __import__("torch").cuda.is_available(),
+                    reason="needs the reference checkout (build container only) and no GPU")
+def test_reference_trainer_reaches_make_through_the_compat_launcher():
+    """The reference's own RPO-LSTM/main.py, unmodified, through `python -m ouzelum_b200.compat`: every import resolves and the
+    script gets as far as isaacgymenvs.make(), which refuses loudly here because there is no GPU (no CPU fallback)."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([sys.executable, "-m", "ouzelum_b200.compat", "/root/reference/isaacgymenvs/RPO-LSTM/main.py",
+                            "--num_envs", "64", "--total_steps", "100"], cwd=tmp, capture_output=True, text=True, timeout=300,
+                           env={**os.environ, "PYTHONPATH": ROOT})
+    assert r.returncode != 0
+    assert "no CUDA device is visible and there is no CPU fallback" in r.stderr, r.stderr[-2000:]
+    assert "isaacgymenvs.make" in r.stderr or "main.py" in r.stderr

@@ -509,3 +509,80 @@ def test_ekf_lee_one_launch_step_tma_path_matches_three_launches(n):
         flips += int((d1 != d2).sum())
     assert flips <= 2, flips
     assert e1.sim.step_count == e2.sim.step_count == 45
+
+
+_MINI_TRAINER = '''
+# A trainer written the way the reference's are (imports, wrappers, loop structure of a CleanRL-style collection pass), used to
+# check the compat launcher on the GPU; it is this repo's own code, not a copy of the reference's.
+import gym
+import isaacgym  # noqa: F401
+import isaacgymenvs
+import torch
+from isaacgymenvs.utils.POMDP import POMDPWrapper
+from torch.utils.tensorboard import SummaryWriter
+
+
+class Stats(gym.Wrapper):
+    def __init__(self, env, device):
+        super().__init__(env)
+        self.num_envs, self.device = getattr(env, "num_envs", 1), device
+
+    def reset(self, **kw):
+        obs = super().reset(**kw)
+        self.ret = torch.zeros(self.num_envs, device=self.device)
+        self.length = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        return obs
+
+    def step(self, action):
+        obs, rew, done, info = super().step(action)
+        self.ret += rew
+        self.length += 1
+        info["r"], info["l"] = self.ret.clone(), self.length.clone()
+        self.ret *= 1 - done
+        self.length *= 1 - done
+        return obs, rew, done, info
+
+
+class ExtractObs(gym.ObservationWrapper):
+    def observation(self, obs):
+        return obs["obs"]
+
+
+envs = isaacgymenvs.make(seed=0, task="Landing", num_envs=512, sim_device="cuda:0", rl_device="cuda:0", graphics_device_id=-1,
+                         headless=True, force_render=True)
+envs = Stats(ExtractObs(envs), torch.device("cuda:0"))
+assert isinstance(envs.action_space, gym.spaces.Box) and envs.action_space.shape == (4,)
+assert envs.observation_space.shape == (13,)
+pomdp = POMDPWrapper(pomdp="flicker", pomdp_prob=0.1)
+writer = SummaryWriter("runs/x")
+obs = envs.reset()
+total = torch.zeros((), device="cuda:0")
+for step in range(48):
+    action = torch.rand(envs.num_envs, 4, device="cuda:0") * 2 - 1
+    obs, rew, done, info = envs.step(action)
+    seen = pomdp.observation(obs)
+    assert seen.shape == obs.shape == (512, 13) and info["r"].shape == (512,) and info["l"].dtype == torch.int32
+    total += rew.sum()
+writer.add_scalar("x", float(total), 0)
+RESULT = dict(total=float(total), steps=int(envs.sim.step_count), dones=int(envs.reset_buf.sum()))
+'''
+
+
+def test_compat_launcher_runs_a_reference_style_trainer(tmp_path):
+    """`python -m ouzelum_b200.compat script.py` in process: a trainer written against gym / isaacgym / isaacgymenvs runs on the
+    GPU through the stand-ins (profiles/r01d_reference_trainer_run.md records the reference's own trainer doing the same)."""
+    import sys
+    from ouzelum_b200 import compat
+    script = tmp_path / "mini_trainer.py"
+    script.write_text(_MINI_TRAINER)
+    before = {k: sys.modules.get(k) for k in ("gym", "gym.spaces", "isaacgym", "isaacgymenvs", "isaacgymenvs.utils",
+                                              "isaacgymenvs.utils.POMDP", "isaacgymenvs.tasks", "torch.utils.tensorboard")}
+    try:
+        g = compat.run(str(script), ["--unused-arg"])
+    finally:
+        for k, v in before.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert g["RESULT"]["steps"] == 48 and g["RESULT"]["total"] > 0
