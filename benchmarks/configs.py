@@ -14,6 +14,13 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# Under torchrun (config 5 on N GPUs: `python -m torch.distributed.run --nproc-per-node N benchmarks/configs.py --only 5`) every
+# rank pins ITS GPU as the only visible device, so it is "cuda:0" everywhere -- the convention the reference's trainers need
+# (they hard-code "cuda:0").  Must happen before torch initialises CUDA.
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+if WORLD > 1:
+    os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("LOCAL_RANK", "0")
 import torch  # noqa: E402
 
 import ouzelum_b200  # noqa: E402
@@ -108,7 +115,7 @@ def config5():
     from ouzelum_b200.pomdp import POMDPWrapper
     from ouzelum_b200.rollout import RecurrentActor, RolloutStorage, collect_rollout, initial_rollout_state
     n, T = 32768, 16
-    cfg = ouzelum_b200.task_config("Landing", n, seed=0, rotorFault={"enable": True})
+    cfg = ouzelum_b200.task_config("Landing", n, seed=0, rotorFault={"enable": True}, envIdBase=RANK * n)
     env = ouzelum_b200.make(seed=0, task="Landing", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
     actor = RecurrentActor().to(DEV)
     store = RolloutStorage(T, n, 13, 4, DEV)
@@ -127,7 +134,15 @@ def config5():
     # env-kernel share: the same number of env steps without the policy
     a = torch.zeros(n, 4, device=DEV)
     dte = timed(lambda: env.step(a), iters * T, 10)
-    return {"config": 5, "workload": "RPO-LSTM rollout collection: Landing task + flicker 0.1 + MLP(13-512-256)+LSTM(256-128) policy, 32768 envs, 16-step rollouts",
+    if WORLD > 1:
+        # envs are sharded over the GPUs with no communication; the job's rate is set by the slowest rank (max time over ranks)
+        import torch.distributed as dist
+        t = torch.tensor([dt_fp32, dt, dt_graph, dte], dtype=torch.float64, device=DEV)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_fp32, dt, dt_graph, dte = (float(x) for x in t.tolist())
+        n = n * WORLD
+    return {"config": 5, "workload": "RPO-LSTM rollout collection: Landing task + flicker 0.1 + MLP(13-512-256)+LSTM(256-128) policy, 32768 envs per GPU, 16-step rollouts",
+            "n_gpus": WORLD, "envs_total": n,
             "env_steps_per_sec": n * T * iters / dt, "us_per_env_step_call": dt / (iters * T) * 1e6,
             "env_steps_per_sec_fp32_simt_policy": n * T * iters / dt_fp32,
             "env_steps_per_sec_cuda_graph": n * T * iters / dt_graph, "us_per_env_step_call_cuda_graph": dt_graph / (iters * T) * 1e6, "policy_matmul": "TF32 tensor cores (torch.backends.cuda.matmul.allow_tf32)",
@@ -139,5 +154,14 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="1,3,4,5")
     args = ap.parse_args()
     fns = {"1": config1, "3": config3, "4": config4, "5": config5}
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(DEV))
+        if args.only != "5":
+            sys.exit("multi-GPU runs of this script are for config 5 only (--only 5)")
     for k in args.only.split(","):
-        print(json.dumps(fns[k]()), flush=True)
+        out = fns[k]()
+        if RANK == 0:
+            print(json.dumps(out), flush=True)
+    if WORLD > 1:
+        dist.destroy_process_group()
