@@ -52,6 +52,22 @@ def config1():
         env.step(acts[k[0] & 15])
         k[0] += 1
     dt = timed(f, steps, 50)
+    env_g = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                              cfg=ouzelum_b200.task_config("Quadcopter", n, seed=0, useCudaGraph=True))
+
+    def fg():
+        env_g.step(acts[k[0] & 15])
+        k[0] += 1
+    dt_g = timed(fg, steps, 50)
+    # the kernel alone: 1000 steps captured in one graph (what a GPU-resident consumer can reach)
+    env_k = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    env_k._launch(acts[0])
+    torch.cuda.synchronize()
+    gk = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gk):
+        for j in range(steps):
+            env_k._launch(acts[j & 15])
+    dt_k = timed(gk.replay, 3, 1) / 3
     from oracle.quadcopter import QuadcopterOracle
     torch.set_num_threads(os.cpu_count() or 1)
     ora = QuadcopterOracle(n, seed=0)
@@ -65,6 +81,8 @@ def config1():
     cdt = time.perf_counter() - t0
     return {"config": 1, "workload": "Quadcopter hover, 256 envs, random actions, 1000 steps (per-step Python launches, no graph)",
             "env_steps_per_sec": n * steps / dt, "us_per_step": dt / steps * 1e6,
+            "env_steps_per_sec_cuda_graph_per_step": n * steps / dt_g, "us_per_step_cuda_graph_per_step": dt_g / steps * 1e6,
+            "env_steps_per_sec_1000_steps_in_one_graph": n * steps / dt_k, "us_per_step_1000_steps_in_one_graph": dt_k / steps * 1e6,
             "cpu_port_env_steps_per_sec": n * cs / cdt, "cpu_cores": os.cpu_count(),
             "cpu_note": "torch-CPU eager oracle of the same step (Isaac Gym CPU pipeline unavailable)"}
 

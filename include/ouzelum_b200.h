@@ -358,8 +358,16 @@ typedef struct ozl_quadcopter_args {
     int32_t substeps;             /* 2                                 */
     float dt, gravity_z, clip_actions, clip_obs;
     float mass, ixx, iyy, izz;
+    uint64_t* step_record;        /* optional: DEVICE step-counter record (ozl_step_record_init).  When set, the kernel takes the
+                                     step index from it and advances it itself -- no host-changing argument, so the launch can be
+                                     captured in a CUDA graph -- and `step` is ignored */
 } ozl_quadcopter_args;
 int ozl_quadcopter_step(const ozl_quadcopter_args* args, void* stream);
+
+/* A stand-alone device step counter for kernels without an env handle: 16 bytes of caller-owned device memory (16-byte aligned),
+ * the same record ozl_step_counter_ptr describes.  `n_envs` fixes how many 128-env blocks retire a work unit per step. */
+int ozl_step_record_init(uint64_t* record_dev, int64_t n_envs, uint64_t step, void* stream);
+int ozl_step_record_read(const uint64_t* record_dev, uint64_t* out, void* stream);   /* synchronises the stream */
 
 const char* ozl_last_error(void);
 int ozl_abi_version(void);

@@ -104,7 +104,7 @@ class OzlQuadcopterArgs(C.Structure):
         ("reset", C.c_void_p), ("progress", C.c_void_p), ("timeout", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
         ("env_id_base", C.c_int64), ("max_episode_length", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_float),
         ("gravity_z", C.c_float), ("clip_actions", C.c_float), ("clip_obs", C.c_float), ("mass", C.c_float),
-        ("ixx", C.c_float), ("iyy", C.c_float), ("izz", C.c_float),
+        ("ixx", C.c_float), ("iyy", C.c_float), ("izz", C.c_float), ("step_record", C.c_void_p),
     ]
 
 
@@ -150,6 +150,8 @@ _SIGS = {
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_husky_step": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),
     "ozl_quadcopter_step": (C.c_int, [C.POINTER(OzlQuadcopterArgs), _P]),
+    "ozl_step_record_init": (C.c_int, [_P, C.c_int64, C.c_uint64, _P]),
+    "ozl_step_record_read": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "ozl_pomdp_observation_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, C.c_int64, C.c_int32,
                                             _P, _P, _P]),
     "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),

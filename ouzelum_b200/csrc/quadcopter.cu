@@ -29,12 +29,11 @@ __device__ __forceinline__ void sincos_small(float x, float& s, float& c) {
     c = 1.0f + x2 * (-0.5f + x2 * (4.1666667e-2f + x2 * (-1.3888889e-3f + x2 * (2.4801587e-5f + x2 * -2.7557319e-7f))));
 }
 
-__global__ void __launch_bounds__(128)
-quadcopter_step_kernel(const QCfg c, const float* __restrict__ actions, float* __restrict__ root13, float* __restrict__ dof_pos,
-                       float* __restrict__ dof_tgt, float* __restrict__ thrust, float* __restrict__ obs, float* __restrict__ rew,
-                       int64_t* __restrict__ reset, int64_t* __restrict__ progress, uint8_t* __restrict__ timeout) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+__device__ __forceinline__ void quadcopter_env(const QCfg& c, const uint64_t step, const int64_t i, const float* __restrict__ actions,
+                                                    float* __restrict__ root13, float* __restrict__ dof_pos, float* __restrict__ dof_tgt,
+                                                    float* __restrict__ thrust, float* __restrict__ obs, float* __restrict__ rew,
+                                                    int64_t* __restrict__ reset, int64_t* __restrict__ progress,
+                                                    uint8_t* __restrict__ timeout) {
     const uint32_t genv = c.env_id_base + (uint32_t)i;
     Env e;
     float* r = root13 + i * 13;
@@ -48,13 +47,13 @@ quadcopter_step_kernel(const QCfg c, const float* __restrict__ actions, float* _
     e.mass = b.mass; e.inv_m = 1.0f / b.mass; e.ixx = b.ixx; e.iyy = b.iyy; e.izz = b.izz; e.arm = 0.f; e.ks = 1.f;
 
     if (rst) {                                                                        // quadcopter.py:280-299
-        const uint4 s0 = draw(c.seed, genv, c.step, P_SPAWN);
+        const uint4 s0 = draw(c.seed, genv, step, P_SPAWN);
         e.p[0] = b.spawn_base[0] + (b.spawn_range[0] * u01(s0.x) + b.spawn_lo[0]);
         e.p[1] = b.spawn_base[1] + (b.spawn_range[1] * u01(s0.y) + b.spawn_lo[1]);
         e.p[2] = b.spawn_base[2] + (b.spawn_range[2] * u01(s0.z) + b.spawn_lo[2]);
         e.q[0] = e.q[1] = e.q[2] = 0.f; e.q[3] = 1.f;
         for (int j = 0; j < 3; ++j) { e.v[j] = 0.f; e.w[j] = 0.f; }
-        const uint4 d0 = draw(c.seed, genv, c.step, P_QDOF0), d1 = draw(c.seed, genv, c.step, P_QDOF1);
+        const uint4 d0 = draw(c.seed, genv, step, P_QDOF0), d1 = draw(c.seed, genv, step, P_QDOF1);
         const uint32_t rr[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         for (int j = 0; j < 8; ++j) dp[j] = 0.4f * u01(rr[j]) + -0.2f;                // torch_rand_float(-0.2, 0.2)
         prog = 0;
@@ -121,9 +120,32 @@ quadcopter_step_kernel(const QCfg c, const float* __restrict__ actions, float* _
     if (timeout) timeout[i] = (over && rs) ? 1 : 0;
 }
 
+__global__ void __launch_bounds__(128)
+quadcopter_step_kernel(const QCfg c, const float* __restrict__ actions, float* __restrict__ root13, float* __restrict__ dof_pos,
+                       float* __restrict__ dof_tgt, float* __restrict__ thrust, float* __restrict__ obs, float* __restrict__ rew,
+                       int64_t* __restrict__ reset, int64_t* __restrict__ progress, uint8_t* __restrict__ timeout,
+                       unsigned long long* __restrict__ step_record, const uint32_t step_pad) {
+    // step index: the host-passed value, or -- graph-capturable -- a device step-counter record (step_counter.cuh) read by one
+    // thread per block and retired with one reduction per block at the end
+    __shared__ uint64_t s_step;
+    if (step_record && threadIdx.x == 0) s_step = read_step(step_record);
+    __syncthreads();
+    const uint64_t step = step_record ? s_step : c.step;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.n) quadcopter_env(c, step, i, actions, root13, dof_pos, dof_tgt, thrust, obs, rew, reset, progress, timeout);
+    __syncthreads();
+    if (step_record && threadIdx.x == 0) retire_units(step_record, 1ull + (blockIdx.x == 0 ? (unsigned long long)step_pad : 0ull));
+}
+
 }  // namespace ozl
 
 using namespace ozl;
+
+static unsigned record_shift(unsigned blocks) {      // 2^shift >= blocks: work units per step, padded to a power of two
+    unsigned l = 0;
+    while ((1ull << l) < blocks) ++l;
+    return l;
+}
 
 extern "C" int ozl_quadcopter_step(const ozl_quadcopter_args* a, void* stream) {
     if (!a) return set_error("ozl_quadcopter_step: args is NULL");
@@ -162,7 +184,30 @@ extern "C" int ozl_quadcopter_step(const ozl_quadcopter_args* a, void* stream) {
     b.inv3 = 1.0f / 3.0f; b.half = 0.5f; b.inv_pi = 1.0f / (float)M_PI;
     const float sb[3] = {0.f, 0.f, 1.f}, sl[3] = {-1.5f, -1.5f, -0.2f}, sr[3] = {3.0f, 3.0f, (float)(1.5 - (-0.2))};
     for (int j = 0; j < 3; ++j) { b.spawn_base[j] = sb[j]; b.spawn_lo[j] = sl[j]; b.spawn_range[j] = sr[j]; }
-    quadcopter_step_kernel<<<(unsigned)((a->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        c, a->actions12, a->root13, a->dof_pos8, a->dof_target8, a->thrust4, a->obs21, a->rew, a->reset, a->progress, a->timeout);
+    const unsigned blocks = (unsigned)((a->n + 127) / 128);
+    if (a->step_record && ((uintptr_t)a->step_record & 15)) return set_error("ozl_quadcopter_step: step_record must be 16-byte aligned");
+    quadcopter_step_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(
+        c, a->actions12, a->root13, a->dof_pos8, a->dof_target8, a->thrust4, a->obs21, a->rew, a->reset, a->progress, a->timeout,
+        (unsigned long long*)a->step_record, (uint32_t)((1ull << record_shift(blocks)) - blocks));
     return check_cuda(cudaGetLastError(), "quadcopter_step_kernel");
+}
+
+// Stand-alone step-counter record (step_counter.cuh) for kernels that have no env handle (ozl_quadcopter_step): 16 bytes of
+// device memory owned by the caller; `n_envs` fixes the number of 128-env blocks per step.
+extern "C" int ozl_step_record_init(uint64_t* record_dev, int64_t n_envs, uint64_t step, void* stream) {
+    if (!record_dev) return set_error("ozl_step_record_init: record is NULL");
+    if (n_envs <= 0) return set_error("ozl_step_record_init: n_envs must be > 0");
+    if ((uintptr_t)record_dev & 15) return set_error("ozl_step_record_init: record must be 16-byte aligned");
+    if (step > kStepBaseMask) return set_error("ozl_step_record_init: step out of range");
+    const unsigned long long w[2] = {step_word0((unsigned long long)step, record_shift((unsigned)((n_envs + 127) / 128))), 0ull};
+    return check_cuda(cudaMemcpyAsync(record_dev, w, sizeof(w), cudaMemcpyHostToDevice, (cudaStream_t)stream), "cudaMemcpyAsync");
+}
+
+extern "C" int ozl_step_record_read(const uint64_t* record_dev, uint64_t* out, void* stream) {
+    if (!record_dev || !out) return set_error("ozl_step_record_read: NULL argument");
+    unsigned long long w[2] = {0, 0};
+    if (check_cuda(cudaMemcpyAsync(w, record_dev, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream), "cudaMemcpyAsync")) return 1;
+    if (check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize")) return 1;
+    *out = step_from_words(w);
+    return 0;
 }

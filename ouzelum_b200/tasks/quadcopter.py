@@ -65,15 +65,40 @@ class Quadcopter(VecTask):
         a.clip_obs = float(min(env.get("clipObservations", math.inf), 3.0e38))
         vc = vehicle_constants()
         a.mass, a.ixx, a.iyy, a.izz = vc["mass"], vc["ixx"], vc["iyy"], vc["izz"]
-        self.step_count = 0
+        # the RNG's time axis lives in a DEVICE step-counter record the kernel reads and advances itself, so a step takes no
+        # host-changing argument and can be replayed from a CUDA graph (env.useCudaGraph)
+        self._step_record = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(lib.ozl_step_record_init(self._step_record.data_ptr(), n, 0, torch.cuda.current_stream().cuda_stream))
+        a.step_record = self._step_record.data_ptr()
+        self.use_cuda_graph = bool(env.get("useCudaGraph", False))
+        self._graph, self._static_actions = None, None
 
-    def _fused_step(self, actions):
+    @property
+    def step_count(self):
+        out = C.c_uint64()
+        check(lib.ozl_step_record_read(self._step_record.data_ptr(), C.byref(out), torch.cuda.current_stream().cuda_stream))
+        return out.value
+
+    def _launch(self, actions):
         a = self._a
         a.actions12, a.obs21, a.rew = actions.data_ptr(), self.obs_buf.data_ptr(), self.rew_buf.data_ptr()
         a.reset, a.progress, a.timeout = self.reset_buf.data_ptr(), self.progress_buf.data_ptr(), self._timeout_u8.data_ptr()
-        a.step = self.step_count
         check(lib.ozl_quadcopter_step(C.byref(a), torch.cuda.current_stream().cuda_stream))
-        self.step_count += 1
+
+    def _fused_step(self, actions):
+        if not self.use_cuda_graph:
+            self._launch(actions)
+            return
+        if self._graph is None:
+            self._static_actions = torch.empty_like(actions)
+            self._static_actions.copy_(actions)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(self._static_actions)
+            self._graph = g
+        self._static_actions.copy_(actions)
+        self._graph.replay()
 
     def reset_idx(self, env_ids):
         self.reset_buf[env_ids] = 1                      # applied inside the next step's kernel (quadcopter.py:304-306)

@@ -149,15 +149,18 @@ def test_lee_landed_closed_loop_reaches_hover_point():
     assert float(root[:, 10:13].abs().max()) < 1.0
 
 
-def test_quadcopter_task_bit_exact_vs_oracle_config1():
-    """BASELINE config 1: Quadcopter hover, 256 envs, random actions U(-1,1) [256,12] from Generator(0)."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_quadcopter_task_bit_exact_vs_oracle_config1(graph):
+    """BASELINE config 1: Quadcopter hover, 256 envs, random actions U(-1,1) [256,12] from Generator(0).  `graph`: the step is
+    replayed from a CUDA graph (the RNG's time axis is a device step-counter record the kernel advances itself)."""
     import ouzelum_b200
     from oracle.quadcopter import QuadcopterOracle, vehicle_constants
     from ouzelum_b200.tasks.quadcopter import vehicle_constants as vc2
     assert vehicle_constants() == vc2()
     assert abs(vehicle_constants()["mass"] - 0.2516) < 1e-3
     n = 256
-    env = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    cfg = ouzelum_b200.task_config("Quadcopter", n, seed=0, useCudaGraph=graph)
+    env = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
     assert env.num_obs == 21 and env.num_acts == 12 and env.max_episode_length == 500
     ora = QuadcopterOracle(n, seed=0)
     g = torch.Generator().manual_seed(0)
@@ -174,6 +177,7 @@ def test_quadcopter_task_bit_exact_vs_oracle_config1():
         assert torch.equal(info["time_outs"].cpu(), ora.timeout_buf), t
         dones += int(d.sum())
     assert dones > 0
+    assert env.step_count == 300 and (env._graph is not None) == graph
     # hover: four equal thrusts of m g / 4 hold altitude
     hover = vehicle_constants()["mass"] * 9.81 / 4
     env.thrusts[:] = hover
