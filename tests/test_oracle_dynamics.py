@@ -92,3 +92,52 @@ def test_reset_ordering_quirk_and_target_resample():
         tg.append(o.target.clone())
     changes = [k for k in range(1, 12) if not torch.equal(tg[k], tg[k - 1])]
     assert changes == [5, 10]            # progress 5 and 10 at the start of steps 6 and 11 (0-based 5, 10)
+
+
+def test_torque_free_tumbling_conserves_angular_momentum_and_energy():
+    """Row P is a restatement without a source to follow (PhysX), so it is also held to the physics: with no thrust and no
+    gravity a tumbling body keeps its world-frame angular momentum L = R I omega_b and its rotational energy up to the drift
+    of a first-order scheme (semi-implicit Euler, h = 5 ms), the drift shrinks with the substep (first-order convergence), the
+    quaternion stays normalised, and the centre of mass moves in a straight line."""
+    n = 64
+    inertia = torch.tensor([float(np.float32(x500.IXX)), float(np.float32(x500.IYY)), float(np.float32(x500.IZZ))], dtype=torch.float64)
+    com_z = float(np.float32(x500.COM_Z))
+
+    def rot(qq):
+        x, y, zz, w = qq[:, 0], qq[:, 1], qq[:, 2], qq[:, 3]
+        return torch.stack([torch.stack([1 - 2 * (y * y + zz * zz), 2 * (x * y - w * zz), 2 * (x * zz + w * y)], 1),
+                            torch.stack([2 * (x * y + w * zz), 1 - 2 * (x * x + zz * zz), 2 * (y * zz - w * x)], 1),
+                            torch.stack([2 * (x * zz - w * y), 2 * (y * zz + w * x), 1 - 2 * (x * x + y * y)], 1)], 1)
+
+    def run(substeps):
+        cfg = default_cfg(n, die_dist=1e9, die_z=-1e9, gravity_z=0.0, max_angvel=1e6, substeps=substeps)
+        o = QuadStepOracle(cfg, dtype=torch.float64)
+        z = torch.zeros(n, 4, dtype=torch.float64)
+        o.step(z)                                                             # applies the initial reset
+        g = torch.Generator().manual_seed(4)
+        q = torch.randn(n, 4, generator=g, dtype=torch.float64)
+        o.root[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+        o.root[:, 7:10] = torch.randn(n, 3, generator=g, dtype=torch.float64)
+        o.root[:, 10:13] = torch.randn(n, 3, generator=g, dtype=torch.float64) * 3.0   # |omega| ~ 5 rad/s, Izz != Ixx
+
+        def invariants():
+            R = rot(o.root[:, 3:7])
+            wb = torch.einsum("nji,nj->ni", R, o.root[:, 10:13])              # body rates = R^T omega_world
+            L = torch.einsum("nij,nj->ni", R, inertia * wb)
+            E = 0.5 * (inertia * wb * wb).sum(1)
+            com = o.root[:, 0:3] + com_z * R[:, :, 2]                         # root -> composite centre of mass
+            return L, E, com
+        L0, E0, c0 = invariants()
+        v_com0 = None
+        for t in range(200):
+            o.step(z)
+            if t == 0:
+                v_com0 = (invariants()[2] - c0) / 0.01
+        L1, E1, c200 = invariants()
+        assert (o.root[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-12
+        assert ((c200 - c0) - v_com0 * 2.0).norm(dim=1).max() < 1e-9, "the centre of mass moves uniformly"
+        return ((L1 - L0).norm(dim=1) / L0.norm(dim=1)).max(), ((E1 - E0).abs() / E0).max()
+    dl2, de2 = run(2)
+    dl8, de8 = run(8)
+    assert dl2 < 5e-2 and de2 < 5e-2, (dl2, de2)              # 2 s of fast tumbling at the task's substep
+    assert dl8 < 0.4 * dl2 and de8 < 0.4 * de2, (dl2, dl8, de2, de8)      # 4x smaller substep: ~4x smaller drift (first order)
