@@ -648,12 +648,13 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     derive_dev_cfg(*cfg, e->dev);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets ~4.75 tiles (measured crossover on B200: generic
-        // 21.5 vs 22.3 us at 393216 envs, 31.6 vs 29.4 us at 524288) (override: OZL_TMA_MIN_TILES, 0 = never)
+    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets ~4.25 tiles (measured crossover on B200, final
+        // kernels: generic 15.0 vs 16.0 us at 262144 envs, 21.5 vs 21.7 us at 393216, 31.2 vs 27.8 us at 524288)
+        // (override: OZL_TMA_MIN_TILES, 0 = never)
         const char* pv = getenv("OZL_PDL");
         e->use_pdl = pv ? atoi(pv) : 1;
         const char* ev = getenv("OZL_TMA_MIN_TILES");
-        e->tma_min_tiles = ev ? atoll(ev) : (19ll * prop.multiProcessorCount * OZL_TMA_MINB) / 4;
+        e->tma_min_tiles = ev ? atoll(ev) : (17ll * prop.multiProcessorCount * OZL_TMA_MINB) / 4;
     }
     const size_t n = (size_t)cfg->num_envs;
     const size_t tiles = (n + kTile - 1) / kTile;
