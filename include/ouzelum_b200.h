@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OZL_ABI_VERSION 1
+#define OZL_ABI_VERSION 2   /* 2: ozl_quadcopter_args.step_record, step-counter record layout (ozl_step_counter_ptr), ozl_host_io */
 
 /* sensor-fault model of isaacgymenvs/utils/POMDP.py:4-42 */
 enum { OZL_POMDP_NONE = 0, OZL_POMDP_FLICKER = 1, OZL_POMDP_NOISE = 2, OZL_POMDP_FLICKER_NOISE = 3 };
