@@ -399,14 +399,40 @@ def run_ours(args):
 
         v_copy = timed(e2e_step)
         v_host = timed(e2e_step_host)
+        env.close()
+        # EnvPool-style pipelining for a consumer that can work on halves: two task objects of n/2 envs on two streams; while the
+        # host consumes half A's results and writes its next actions, half B's step (action reads, compute, PCIe write-back) runs
+        half = n // 2
+        halves = []
+        for hx in range(2):
+            tch = ouzelum_b200.task_config("Ouzelum", half, rotorFault={"enable": True}, seed=args.seed, envIdBase=rank * n + hx * half)
+            eh = ouzelum_b200.make(seed=args.seed, task="Ouzelum", num_envs=half, sim_device=str(dev), rl_device=str(dev),
+                                   headless=True, cfg=tch)
+            eh.reset()
+            halves.append((eh, torch.cuda.Stream(device=dev), [(torch.rand(half, 4) * 2 - 1).pin_memory() for _ in range(4)]))
+        for eh, st_, ah in halves:
+            eh.step_host_async(ah[0], st_)
+        for eh, _, _ in halves:
+            eh.step_host_wait()
+
+        def e2e_step_halves(k):
+            # one "step" = both halves advanced once (n env-steps); each wait is followed at once by that half's next launch
+            for eh, st_, ah in halves:
+                eh.step_host_wait()
+                eh.step_host_async(ah[k & 3], st_)
+        v_halves = timed(e2e_step_halves)
+        for eh, _, _ in halves:
+            eh.step_host_wait()
+            eh.close()
         e2e = {"value": v_host, "unit": UNIT,
                "h2d_bytes_per_step": world * h_act[0].numel() * 4,
                "d2h_bytes_per_step": world * (n * 13 * 4 + n * 4 + n),
                "api": "ouzelum_b200.make(...).step_host(pinned actions) -> pinned (obs, reward, done): one launch, zero-copy PCIe reads/writes inside the kernel, stream sync",
+               "value_pipelined_two_halves": v_halves,
+               "pipelined_two_halves": "two task objects of n/2 envs on two streams, step_host_async / step_host_wait: one half's PCIe write-back overlaps the other half's step (for consumers that can work on halves; not the reference's synchronous step)",
                "value_with_explicit_copies": v_copy,
                "explicit_copies": {"api": "make(...).step(device actions) bracketed by cudaMemcpyAsync pinned->device / device->pinned + sync",
                                    "d2h_bytes_per_step": world * (h_obs.numel() * 4 + h_rew.numel() * 4 + h_rst.numel() * 8)}}
-        env.close()
 
     # ---- roofline of the dominant (only) kernel, live, at an L2-exceeding size ------------------------------------
     roofline = roofline_wl = None

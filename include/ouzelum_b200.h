@@ -128,6 +128,10 @@ typedef struct ozl_host_io {
     float* ep_ret;              /* [N] device or NULL */
 } ozl_host_io;
 int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream);
+/* The two halves of ozl_step_host_sync, for a host consumer that pipelines several handles on several streams: launch only, and
+ * a bare cudaStreamSynchronize (so that a binding needs no CUDA runtime of its own). */
+int ozl_step_host_launch(ozl_env* env, const ozl_host_io* io, void* stream);
+int ozl_stream_sync(void* stream);
 
 /* Same step with the target supplied by the caller every step instead of being re-sampled in-kernel: the landing
  * family, whose target rides on a ground vehicle (tasks/landing.py:373-374, lando.py, landed.py).  target3 [N,3] f32. */

@@ -744,11 +744,19 @@ extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs
                        "ozl_step_host", done_host, 0);
 }
 
+extern "C" int ozl_step_host_launch(ozl_env* env, const ozl_host_io* io, void* stream) {
+    if (!io) return set_error("ozl_step_host_launch: io is NULL");
+    return ozl_step_host(env, io->actions_host, io->obs_host, io->rew_host, io->done_host, io->reset, io->progress, io->timeout,
+                         io->ep_ret, stream);
+}
+
 extern "C" int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream) {
     if (!io) return set_error("ozl_step_host_sync: io is NULL");
-    if (ozl_step_host(env, io->actions_host, io->obs_host, io->rew_host, io->done_host, io->reset, io->progress, io->timeout,
-                      io->ep_ret, stream))
-        return 1;
+    if (ozl_step_host_launch(env, io, stream)) return 1;
+    return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+}
+
+extern "C" int ozl_stream_sync(void* stream) {
     return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
 }
 

@@ -115,6 +115,22 @@ class X500Task(VecTask):
             _lib.check(1)
         return self._h_obs, self._h_rew, self._h_done
 
+    def step_host_async(self, actions_host, stream=None):
+        """Launch-only half of `step_host` (EnvPool-style pipelining: a CPU consumer that splits its envs over two task objects can
+        let one object's PCIe write-back overlap the other's action reads and compute).  The results are valid after
+        `step_host_wait()`.  `stream`: a torch.cuda.Stream to launch on (default: the current stream)."""
+        io = self._host_io.get(actions_host.data_ptr())
+        if io is None:
+            io = self._make_host_io(actions_host)
+        self._host_stream = stream.cuda_stream if stream is not None else torch._C._cuda_getCurrentRawStream(self.sim.index)
+        if _lib.lib.ozl_step_host_launch(self.sim._h, io, self._host_stream):
+            _lib.check(1)
+
+    def step_host_wait(self):
+        if _lib.lib.ozl_stream_sync(self._host_stream):
+            _lib.check(1)
+        return self._h_obs, self._h_rew, self._h_done
+
     def _make_host_io(self, actions_host):
         """Argument block of ozl_step_host_sync for one actions buffer, validated once and cached by address."""
         import ctypes as C

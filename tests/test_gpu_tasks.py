@@ -271,6 +271,16 @@ def test_step_host_zero_copy_matches_device_step():
     assert torch.equal(e1.reset_buf, e2.reset_buf) and torch.equal(e1.progress_buf, e2.progress_buf)
     with pytest.raises(ValueError):
         e2.step_host(torch.zeros(n, 4))          # not pinned
+    # launch / wait halves of the same call, on a side stream (pipelining several task objects from one host thread)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for t in range(20):
+        a = (torch.rand(n, 4, generator=g) * 2 - 1).pin_memory()
+        o1, r1, d1, _ = e1.step(a.to(DEV))
+        e2.step_host_async(a, side)
+        ho, hr, hd = e2.step_host_wait()
+        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu().to(torch.uint8), hd), t
+    assert e1.sim.step_count == e2.sim.step_count == 80
 
 
 @pytest.mark.parametrize("graph,fused_step", [(False, False), (True, False), (False, True), (True, True)])
