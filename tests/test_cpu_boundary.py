@@ -170,7 +170,7 @@ def test_c_abi_argument_errors_need_no_gpu(lib):
     assert L.ozl_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0 and "abi_version" in msg()
 
 
-def test_compat_shims_resolve_the_reference_trainer_imports(lib):
+def test_compat_shims_resolve_the_reference_trainer_imports(lib, tmp_path):
     """ouzelum_b200.compat (SURVEY 8f rank 1): the module names a reference trainer imports resolve to this package's pieces;
     the gym stand-in has gym 0.24's Wrapper / ObservationWrapper semantics (what RPO-LSTM/utils.py:4-39 subclasses)."""
     import importlib
@@ -181,7 +181,7 @@ def test_compat_shims_resolve_the_reference_trainer_imports(lib):
                                               "isaacgymenvs.utils.POMDP", "isaacgymenvs.tasks", "torch.utils.tensorboard")}
     try:
         installed = compat.install()
-        assert {"isaacgym", "isaacgymenvs", "gym"} <= set(installed)             # none of them exists in this image
+        assert {"isaacgym", "isaacgymenvs", "gym"} <= set(installed)             # none of them exists in this image (tensorboard does)
         import gym
         import isaacgym  # noqa: F401
         import isaacgymenvs
@@ -189,7 +189,7 @@ def test_compat_shims_resolve_the_reference_trainer_imports(lib):
         from torch.utils.tensorboard import SummaryWriter
         assert isaacgymenvs.make is ouzelum_b200.make
         assert POMDPWrapper is importlib.import_module("ouzelum_b200.pomdp").POMDPWrapper
-        SummaryWriter("x").add_scalar("a", 1.0, 0)
+        SummaryWriter(str(tmp_path / "tb")).add_scalar("a", 1.0, 0)     # the real one if tensorboard is installed, else the no-op stand-in
 
         class Inner:
             num_envs, action_space = 3, gym.spaces.Box(-1.0, 1.0, (4,))

@@ -568,7 +568,8 @@ envs = Stats(ExtractObs(envs), torch.device("cuda:0"))
 assert isinstance(envs.action_space, gym.spaces.Box) and envs.action_space.shape == (4,)
 assert envs.observation_space.shape == (13,)
 pomdp = POMDPWrapper(pomdp="flicker", pomdp_prob=0.1)
-writer = SummaryWriter("runs/x")
+import tempfile
+writer = SummaryWriter(tempfile.mkdtemp())
 obs = envs.reset()
 total = torch.zeros((), device="cuda:0")
 for step in range(48):
