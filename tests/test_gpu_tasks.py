@@ -601,3 +601,22 @@ def test_compat_launcher_runs_a_reference_style_trainer(tmp_path):
             else:
                 sys.modules[k] = v
     assert g["RESULT"]["steps"] == 48 and g["RESULT"]["total"] > 0
+
+
+def test_rl_device_cpu_returns_host_tensors_like_the_reference():
+    """vec_task.py:353-359: obs / reward / reset / time_outs are returned on `rl_device`; with rl_device="cpu" the trainer gets CPU
+    tensors (and may pass CPU actions), the simulation stays on the GPU.  Values equal the rl_device == sim_device run."""
+    import ouzelum_b200
+    n = 300
+    e_gpu = ouzelum_b200.make(seed=4, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    e_cpu = ouzelum_b200.make(seed=4, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device="cpu", headless=True)
+    assert e_cpu.reset()["obs"].device.type == "cpu" and e_cpu.zero_actions().device.type == "cpu"
+    g = torch.Generator().manual_seed(1)
+    for t in range(25):
+        a = torch.rand(n, 4, generator=g) * 2 - 1                        # CPU actions
+        o1, r1, d1, i1 = e_gpu.step(a.to(DEV))
+        o2, r2, d2, i2 = e_cpu.step(a)
+        for x in (o2["obs"], r2, d2, i2["time_outs"]):
+            assert x.device.type == "cpu"
+        assert torch.equal(o1["obs"].cpu(), o2["obs"]) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2), t
+        assert d2.dtype == torch.int64 and i2["time_outs"].dtype == torch.bool
