@@ -620,3 +620,28 @@ def test_rl_device_cpu_returns_host_tensors_like_the_reference():
             assert x.device.type == "cpu"
         assert torch.equal(o1["obs"].cpu(), o2["obs"]) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2), t
         assert d2.dtype == torch.int64 and i2["time_outs"].dtype == torch.bool
+
+
+def test_reset_idx_and_reset_done_surface():
+    """VecTask.reset_idx / reset_done (vec_task.py:391-406, ouzelum.py:192-216): a requested reset takes effect in the next step's
+    pre-physics phase, exactly where the reference applies the resets it decided itself -- the env is re-spawned inside the spawn
+    box, its progress restarts and its thrust command is zeroed for that step."""
+    import ouzelum_b200
+    n = 64
+    env = ouzelum_b200.make(seed=2, task="Ouzelum", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
+    a = torch.full((n, 4), 0.3, device=DEV)
+    for _ in range(5):
+        env.step(a)
+    assert int(env.reset_buf.sum()) == 0 and bool((env.progress_buf == 5).all())
+    ids = torch.tensor([3, 17, 40], device=DEV)
+    env.reset_idx(ids)
+    obs_dict, done_ids = env.reset_done()
+    assert sorted(done_ids.tolist()) == [3, 17, 40] and obs_dict["obs"].shape == (n, 13)
+    env.step(a)
+    prog = env.progress_buf.cpu()
+    assert prog[ids.cpu()].tolist() == [1, 1, 1] and int((prog == 6).sum()) == n - 3
+    pos, thrust = env.root_positions.cpu(), env.thrusts.cpu()
+    for i in ids.tolist():
+        assert -1.5 <= pos[i, 0] <= 1.5 and -1.5 <= pos[i, 1] <= 1.5 and 0.75 <= pos[i, 2] <= 2.55      # spawn box, one free-fall step
+        assert float(thrust[i].abs().max()) == 0.0                                                 # ouzelum.py:247-248
+    assert float(thrust[0].min()) > 0.0
