@@ -17,15 +17,17 @@ bound the float32 integration error), one `VecTask.step` of the reference's x500
 replaced by the explicit single-rigid-body integrator of SURVEY.md section 8a row P ("parity
 unpinned" against PhysX; this file IS the contract the CUDA kernel is held to):
   per substep h = dt/substeps, semi-implicit Euler, wrench converted LOCAL->world once per control
-  step and held, |omega| clamped to 4*pi after the velocity update, PhysX-style closed-form
-  quaternion update q <- normalize(exp(h/2 * omega_world) * q) with sin/cos evaluated by fixed
-  polynomials (|h/2*omega| <= 0.032 rad: truncation < 1e-14, far below float32 eps).
+  step and held, body-frame angular velocity carried across the substeps, |omega| clamped to 4*pi
+  after the velocity update, closed-form quaternion update q <- normalize(q * exp(h/2 * omega_body))
+  (row P's formula) with sin/cos evaluated by fixed polynomials (|h/2*omega| <= 0.032 rad: truncation
+  < 1e-14, far below float32 eps) and the normalisation by one Newton step of 1/sqrt about 1.
 
 Random draws follow oracle/philox.py (counter-based; SURVEY.md 8a row R explains why the
 reference's global-generator stream cannot be reproduced).
 
 float32 mode is written so that every +,-,*,/,sqrt is individually rounded in exactly the order the
-CUDA kernel (compiled with -fmad=false) performs them => the kernel is expected to match this
+CUDA kernel (compiled with -fmad=false) performs them; the integrator's explicit fused multiply-adds
+(fmaf in the kernel) are reproduced with an exactly rounded `fma()` => the kernel is expected to match this
 oracle BIT-EXACTLY, which is what makes the integer outputs (reset / timeout flags over long
 roll-outs) exactly comparable.
 """
@@ -131,28 +133,53 @@ def compute_observations(root_states, target_root_positions):
     return obs
 
 
+def fma(a, b, c):
+    """Fused multiply-add a*b + c with ONE rounding, element-wise on torch tensors (python scalars allowed).
+
+    float32: the product of two float32 values is exact in float64 (48 <= 53 bits); the float64 sum is then rounded TO ODD
+    (error-free TwoSum; if the sum is inexact and its last mantissa bit is even, step one ulp towards the exact value), and a
+    round-to-odd value with >= 2 spare bits rounds to float32 exactly like the infinitely precise result (Boldo & Melquiond
+    2008).  This matches CUDA's fmaf / FFMA and C's fmaf bit for bit.  float64 (error-bounding mode only): plain a*b + c."""
+    ts = [t for t in (a, b, c) if isinstance(t, torch.Tensor)]
+    dt = ts[0].dtype
+    if dt == torch.float64:
+        return a * b + c
+    f = lambda t: (t.detach().numpy() if isinstance(t, torch.Tensor) else np.float32(t)).astype(np.float64)
+    p = f(a) * f(b)
+    cd = f(c)
+    s = np.asarray(p + cd, dtype=np.float64)
+    bb = s - p
+    err = (p - (s - bb)) + (cd - bb)
+    si = s.view(np.int64) if s.ndim else np.array(s).reshape(1).view(np.int64)
+    s1 = s if s.ndim else s.reshape(1)
+    inexact = np.isfinite(s1) & (np.broadcast_to(err, s1.shape) != 0)
+    grow = (np.broadcast_to(err, s1.shape) > 0) == (s1 > 0)              # the exact value lies further from zero than s
+    adj = np.where(inexact & ((si & 1) == 0), np.where(grow, 1, -1), 0).astype(np.int64)
+    out = (si + adj).view(np.float64).astype(np.float32)
+    return torch.from_numpy(out.reshape(s.shape) if s.ndim else out.reshape(()))
+
+
 def quat_to_R(q):
-    """xyzw unit quaternion -> rotation matrix entries (dict r[i][j]); fixed op order shared with the kernel."""
+    """xyzw unit quaternion -> rotation matrix entries r[i][j]; fixed op order shared with the kernel (quad_env.cuh)."""
     x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    xx, yy, zz = x * x, y * y, z * z
-    xy, xz, yz = x * y, x * z, y * z
-    wx, wy, wz = w * x, w * y, w * z
-    r = [[1.0 - 2.0 * (yy + zz), 2.0 * (xy - wz), 2.0 * (xz + wy)],
-         [2.0 * (xy + wz), 1.0 - 2.0 * (xx + zz), 2.0 * (yz - wx)],
-         [2.0 * (xz - wy), 2.0 * (yz + wx), 1.0 - 2.0 * (xx + yy)]]
-    return r
+    x2, y2, z2 = x + x, y + y, z + z
+    wx, wy, wz = x2 * w, y2 * w, z2 * w
+    a, b = fma(-y2, y, 1.0), fma(-x2, x, 1.0)
+    return [[fma(-z2, z, a), fma(x2, y, -wz), fma(x2, z, wy)],
+            [fma(x2, y, wz), fma(-z2, z, b), fma(y2, z, -wx)],
+            [fma(x2, z, -wy), fma(y2, z, wx), fma(-y2, y, b)]]
 
 
 def _matvec(r, v):
-    return [(r[i][0] * v[0] + r[i][1] * v[1]) + r[i][2] * v[2] for i in range(3)]
+    return [fma(r[i][2], v[2], fma(r[i][1], v[1], r[i][0] * v[0])) for i in range(3)]
 
 
 def _matTvec(r, v):
-    return [(r[0][i] * v[0] + r[1][i] * v[1]) + r[2][i] * v[2] for i in range(3)]
+    return [fma(r[2][i], v[2], fma(r[1][i], v[1], r[0][i] * v[0])) for i in range(3)]
 
 
 def _cross(a, b):
-    return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+    return [fma(a[1], b[2], -(a[2] * b[1])), fma(a[2], b[0], -(a[0] * b[2])), fma(a[0], b[1], -(a[1] * b[0]))]
 
 
 class QuadStepOracle:
@@ -357,6 +384,7 @@ class QuadStepOracle:
 
     # ------------------------------------------------------------------ rigid body
     def _simulate(self, force, wrench=None, body_force=None):
+        """Integrator "row P" v2 -- same operations, same order as `simulate()` in ouzelum_b200/csrc/quad_env.cuh."""
         cfg, c = self.cfg, self._c
         root, P = self.root, self.params
         p = [root[:, j] for j in range(0, 3)]
@@ -365,7 +393,10 @@ class QuadStepOracle:
         w = [root[:, j] for j in range(10, 13)]
         inv_m = 1.0 / P[:, 0]
         inertia = [P[:, 1], P[:, 2], P[:, 3]]
-        inv_i = [1.0 / P[:, 1], 1.0 / P[:, 2], 1.0 / P[:, 3]]
+        h = c(cfg["dt"] / cfg["substeps"])
+        hh = c(0.5 * (cfg["dt"] / cfg["substeps"]))
+        hh2 = hh * hh
+        hi = [h * (1.0 / P[:, 1]), h * (1.0 / P[:, 2]), h * (1.0 / P[:, 3])]
         arm, cz = P[:, 4], c(cfg["com_z"])
         if wrench is not None:
             fz, tau_b = wrench
@@ -379,53 +410,60 @@ class QuadStepOracle:
         b3 = [R[0][2], R[1][2], R[2][2]]
         fw = _matvec(R, body_force) if body_force is not None else [b3[j] * fz for j in range(3)]
         tau_w = _matvec(R, tau_b)
+        g = [c(0.0), c(0.0), c(cfg["gravity_z"])]
+        kdm = c(cfg["lin_drag"]) * inv_m
+        aw = [fma(fw[j], inv_m, g[j]) for j in range(3)]
         # root (base-link origin) -> composite COM
         rc = [cz * b3[j] for j in range(3)]
         x = [p[j] + rc[j] for j in range(3)]
         wxr = _cross(w, rc)
         v = [v[j] + wxr[j] for j in range(3)]
-        h = c(cfg["dt"] / cfg["substeps"])
-        hh = c(0.5 * (cfg["dt"] / cfg["substeps"]))
-        g = [c(0.0), c(0.0), c(cfg["gravity_z"])]
-        kd = c(cfg["lin_drag"])
+        wb = _matTvec(R, w)
+        tb = list(tau_b)
         wmax, wmax2 = c(cfg["max_angvel"]), c(cfg["max_angvel"] ** 2)
-        for _ in range(int(cfg["substeps"]) * int(cfg["control_freq_inv"])):
-            # linear velocity
+        nsub = int(cfg["substeps"]) * int(cfg["control_freq_inv"])
+        one = torch.ones_like(inv_m)
+        for s_ in range(nsub):
+            # linear velocity (world), position
             for j in range(3):
-                acc = ((fw[j] - kd * v[j]) * inv_m) + g[j]
-                v[j] = v[j] + h * acc
-            # angular velocity (Euler's equations in the body frame)
-            wb = _matTvec(R, w)
-            tb = _matTvec(R, tau_w)
+                v[j] = fma(h, fma(-kdm, v[j], aw[j]), v[j])
+                x[j] = fma(h, v[j], x[j])
+            # angular velocity: Euler's equations in the body frame
             iw = [inertia[j] * wb[j] for j in range(3)]
             gy = _cross(wb, iw)
-            wb = [wb[j] + h * ((tb[j] - gy[j]) * inv_i[j]) for j in range(3)]
-            w = _matvec(R, wb)
-            n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]
-            scale = torch.where(n2 > wmax2, wmax / ieee_sqrt(n2), torch.ones_like(n2))
-            w = [w[j] * scale for j in range(3)]
-            # pose
-            x = [x[j] + h * v[j] for j in range(3)]
-            n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]
-            th2 = (hh * hh) * n2                                  # (h/2 |w|)^2
+            wb = [fma(hi[j], tb[j] - gy[j], wb[j]) for j in range(3)]
+            n2 = fma(wb[2], wb[2], fma(wb[1], wb[1], wb[0] * wb[0]))
+            over = n2 > wmax2
+            scale = torch.where(over, wmax / ieee_sqrt(n2), one)
+            wb = [torch.where(over, wb[j] * scale, wb[j]) for j in range(3)]
+            n2 = torch.where(over, fma(wb[2], wb[2], fma(wb[1], wb[1], wb[0] * wb[0])), n2)
+            # attitude: q <- normalize(q (x) (k w_b, cos))
+            th2 = hh2 * n2                                        # (h/2 |w|)^2
             if self.exact_trig:
                 th = ieee_sqrt(th2)
                 sinc = torch.where(th > 0, torch.sin(th) / torch.where(th > 0, th, torch.ones_like(th)), torch.ones_like(th))
                 cs = torch.cos(th)
             else:
-                sinc = 1.0 + th2 * (c(-1.0 / 6.0) + th2 * c(1.0 / 120.0))
-                cs = 1.0 + th2 * (c(-0.5) + th2 * (c(1.0 / 24.0) + th2 * c(-1.0 / 720.0)))
+                sinc = fma(th2, fma(th2, c(1.0 / 120.0), c(-1.0 / 6.0)), 1.0)
+                cs = fma(th2, fma(th2, fma(th2, c(-1.0 / 720.0), c(1.0 / 24.0)), c(-0.5)), 1.0)
             k = hh * sinc
-            px_, py_, pz_ = k * w[0], k * w[1], k * w[2]
+            dx, dy, dz = k * wb[0], k * wb[1], k * wb[2]
             qx, qy, qz, qw = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-            nx = (qw * px_ + (py_ * qz - pz_ * qy)) + qx * cs
-            ny = (qw * py_ + (pz_ * qx - px_ * qz)) + qy * cs
-            nz = (qw * pz_ + (px_ * qy - py_ * qx)) + qz * cs
-            nw = qw * cs - ((px_ * qx + py_ * qy) + pz_ * qz)
-            inv = 1.0 / ieee_sqrt(((nx * nx + ny * ny) + nz * nz) + nw * nw)
+            nx = fma(qw, dx, fma(cs, qx, fma(qy, dz, -(qz * dy))))
+            ny = fma(qw, dy, fma(cs, qy, fma(qz, dx, -(qx * dz))))
+            nz = fma(qw, dz, fma(cs, qz, fma(qx, dy, -(qy * dx))))
+            nw = fma(qw, cs, -fma(qx, dx, fma(qy, dy, qz * dz)))
+            s2 = fma(nx, nx, fma(ny, ny, fma(nz, nz, nw * nw)))
+            if self.exact_trig:
+                inv = 1.0 / ieee_sqrt(s2)
+            else:
+                inv = fma(c(-0.5), s2, 1.5)                       # one Newton step of 1/sqrt about s2 = 1
             q = torch.stack([nx * inv, ny * inv, nz * inv, nw * inv], -1)
             R = quat_to_R(q)
-        # composite COM -> root (base-link origin): p = x - R c ; v_root = v_com - w x (R c)
+            if s_ + 1 < nsub:
+                tb = _matTvec(R, tau_w)                           # held world-frame torque seen from the new attitude
+        # body rates -> world; composite COM -> root (base-link origin): p = x - R c ; v_root = v_com - w x (R c)
+        w = _matvec(R, wb)
         b3 = [R[0][2], R[1][2], R[2][2]]
         rc = [cz * b3[j] for j in range(3)]
         wxr = _cross(w, rc)

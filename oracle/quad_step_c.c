@@ -4,7 +4,8 @@
  *   isaacgymenvs/tasks/base/vec_task.py:313-359, isaacgymenvs/tasks/ouzelum.py:180-332,
  *   isaacgymenvs/utils/torch_jit_utils.py:66-71,198-208, isaacgymenvs/utils/POMDP.py:23-42;
  *   gym.simulate -> the integrator of SURVEY.md 8a row P.
- * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC -Iinclude oracle/quad_step_c.c -lm   (oracle/c_oracle.py)
+ * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC -Iinclude oracle/quad_step_c.c -lm   (oracle/c_oracle.py;
+ * -mfma only lets the EXPLICIT fmaf calls compile to one instruction -- without it glibc's exact software fmaf is used)
  */
 #include <math.h>
 #include <stdint.h>
@@ -30,26 +31,29 @@ static void draw(uint64_t seed, uint32_t env, uint64_t step, uint32_t purpose, u
 static float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 
 typedef struct {
-    float h, hh, max_angvel2, inv3, half, inv_pi, flicker_p, noise_lo, noise_range;
+    float h, hh, hh2, max_angvel2, inv3, half, inv_pi, flicker_p, noise_lo, noise_range;
     float sinc_c1, sinc_c2, cos_c1, cos_c2, cos_c3;
     int nsub;
 } derived_t;
 
+/* integrator arithmetic "row P" v2: single IEEE operations and explicit fmaf, in the order of quad_env.cuh */
 static void quat_to_R(const float q[4], float R[3][3]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-    R[0][0] = 1.0f - 2.0f * (yy + zz); R[0][1] = 2.0f * (xy - wz); R[0][2] = 2.0f * (xz + wy);
-    R[1][0] = 2.0f * (xy + wz); R[1][1] = 1.0f - 2.0f * (xx + zz); R[1][2] = 2.0f * (yz - wx);
-    R[2][0] = 2.0f * (xz - wy); R[2][1] = 2.0f * (yz + wx); R[2][2] = 1.0f - 2.0f * (xx + yy);
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float wx = x2 * w, wy = y2 * w, wz = z2 * w;
+    const float a = fmaf(-y2, y, 1.0f), b = fmaf(-x2, x, 1.0f);
+    R[0][0] = fmaf(-z2, z, a);  R[0][1] = fmaf(x2, y, -wz); R[0][2] = fmaf(x2, z, wy);
+    R[1][0] = fmaf(x2, y, wz);  R[1][1] = fmaf(-z2, z, b);  R[1][2] = fmaf(y2, z, -wx);
+    R[2][0] = fmaf(x2, z, -wy); R[2][1] = fmaf(y2, z, wx);  R[2][2] = fmaf(-y2, y, b);
 }
 static void mv(float R[3][3], const float v[3], float o[3]) {
-    for (int i = 0; i < 3; ++i) o[i] = (R[i][0] * v[0] + R[i][1] * v[1]) + R[i][2] * v[2];
+    for (int i = 0; i < 3; ++i) o[i] = fmaf(R[i][2], v[2], fmaf(R[i][1], v[1], R[i][0] * v[0]));
 }
 static void mtv(float R[3][3], const float v[3], float o[3]) {
-    for (int i = 0; i < 3; ++i) o[i] = (R[0][i] * v[0] + R[1][i] * v[1]) + R[2][i] * v[2];
+    for (int i = 0; i < 3; ++i) o[i] = fmaf(R[2][i], v[2], fmaf(R[1][i], v[1], R[0][i] * v[0]));
 }
 static void cross3(const float a[3], const float b[3], float o[3]) {
-    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    o[0] = fmaf(a[1], b[2], -(a[2] * b[1])); o[1] = fmaf(a[2], b[0], -(a[0] * b[2])); o[2] = fmaf(a[0], b[1], -(a[1] * b[0]));
 }
 
 /* state arrays (AoS, caller-owned): root [n,13], thrust [n,4], target [n,3], ep_ret [n], params [n,7] =
@@ -59,7 +63,7 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
                      int64_t* progress, uint8_t* timeout) {
     derived_t d;
     const double h = (double)c->dt / (double)c->substeps;
-    d.h = (float)h; d.hh = (float)(0.5 * h);
+    d.h = (float)h; d.hh = (float)(0.5 * h); d.hh2 = d.hh * d.hh;
     d.max_angvel2 = (float)((double)c->max_angvel * (double)c->max_angvel);
     d.inv3 = 1.0f / 3.0f; d.half = 0.5f; d.inv_pi = 1.0f / (float)M_PI;
     d.flicker_p = (c->pomdp_mode == 3) ? 0.1f : c->pomdp_prob;
@@ -122,45 +126,51 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
         }
         const int fault_active = c->fault_mode && prog >= (int64_t)fault[i * 2 + 1];
         if (fault_active) F[fault[i * 2]] = F[fault[i * 2]] * pr[6];
-        /* rigid body */
+        /* rigid body (body-frame angular velocity across the substeps, right-multiplied attitude update) */
         const float inv_m = 1.0f / pr[0];
-        const float inertia[3] = {pr[1], pr[2], pr[3]}, inv_i[3] = {1.0f / pr[1], 1.0f / pr[2], 1.0f / pr[3]};
+        const float inertia[3] = {pr[1], pr[2], pr[3]};
+        const float hi[3] = {d.h * (1.0f / pr[1]), d.h * (1.0f / pr[2]), d.h * (1.0f / pr[3])};
         const float fz = ((F[0] + F[1]) + F[2]) + F[3];
         const float tau_b[3] = {pr[4] * (((F[1] - F[0]) + F[2]) - F[3]), pr[4] * (((F[1] - F[0]) - F[2]) + F[3]),
                                 c->yaw_km * (((F[2] - F[0]) - F[1]) + F[3])};
-        float R[3][3], fw[3], tau_w[3], rc[3], x[3], t3[3];
+        float R[3][3], fw[3], tau_w[3], aw[3], rc[3], x[3], t3[3], wb[3], tb[3];
         quat_to_R(q, R);
         for (int j = 0; j < 3; ++j) fw[j] = R[j][2] * fz;
         mv(R, tau_b, tau_w);
-        for (int j = 0; j < 3; ++j) { rc[j] = c->com_z * R[j][2]; x[j] = p[j] + rc[j]; }
-        cross3(w, rc, t3);
-        for (int j = 0; j < 3; ++j) v[j] = v[j] + t3[j];
         const float g[3] = {0.0f, 0.0f, c->gravity_z};
+        const float kdm = c->lin_drag * inv_m;
+        for (int j = 0; j < 3; ++j) { aw[j] = fmaf(fw[j], inv_m, g[j]); rc[j] = c->com_z * R[j][2]; x[j] = p[j] + rc[j]; }
+        cross3(w, rc, t3);
+        for (int j = 0; j < 3; ++j) { v[j] = v[j] + t3[j]; tb[j] = tau_b[j]; }
+        mtv(R, w, wb);
         for (int s = 0; s < d.nsub; ++s) {
-            for (int j = 0; j < 3; ++j) { const float acc = ((fw[j] - c->lin_drag * v[j]) * inv_m) + g[j]; v[j] = v[j] + d.h * acc; }
-            float wb[3], tb[3], iw[3], gy[3];
-            mtv(R, w, wb); mtv(R, tau_w, tb);
+            for (int j = 0; j < 3; ++j) { v[j] = fmaf(d.h, fmaf(-kdm, v[j], aw[j]), v[j]); x[j] = fmaf(d.h, v[j], x[j]); }
+            float iw[3], gy[3];
             for (int j = 0; j < 3; ++j) iw[j] = inertia[j] * wb[j];
             cross3(wb, iw, gy);
-            for (int j = 0; j < 3; ++j) wb[j] = wb[j] + d.h * ((tb[j] - gy[j]) * inv_i[j]);
-            mv(R, wb, w);
-            float n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
-            if (n2 > d.max_angvel2) { const float sc = c->max_angvel / sqrtf(n2); for (int j = 0; j < 3; ++j) w[j] = w[j] * sc; }
-            for (int j = 0; j < 3; ++j) x[j] = x[j] + d.h * v[j];
-            n2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
-            const float th2 = (d.hh * d.hh) * n2;
-            const float sinc = 1.0f + th2 * (d.sinc_c1 + th2 * d.sinc_c2);
-            const float cs = 1.0f + th2 * (d.cos_c1 + th2 * (d.cos_c2 + th2 * d.cos_c3));
+            for (int j = 0; j < 3; ++j) wb[j] = fmaf(hi[j], tb[j] - gy[j], wb[j]);
+            float n2 = fmaf(wb[2], wb[2], fmaf(wb[1], wb[1], wb[0] * wb[0]));
+            if (n2 > d.max_angvel2) {
+                const float sc = c->max_angvel / sqrtf(n2);
+                for (int j = 0; j < 3; ++j) wb[j] = wb[j] * sc;
+                n2 = fmaf(wb[2], wb[2], fmaf(wb[1], wb[1], wb[0] * wb[0]));
+            }
+            const float th2 = d.hh2 * n2;
+            const float sinc = fmaf(th2, fmaf(th2, d.sinc_c2, d.sinc_c1), 1.0f);
+            const float cs = fmaf(th2, fmaf(th2, fmaf(th2, d.cos_c3, d.cos_c2), d.cos_c1), 1.0f);
             const float k = d.hh * sinc;
-            const float px = k * w[0], py = k * w[1], pz = k * w[2];
-            const float nx = (q[3] * px + (py * q[2] - pz * q[1])) + q[0] * cs;
-            const float ny = (q[3] * py + (pz * q[0] - px * q[2])) + q[1] * cs;
-            const float nz = (q[3] * pz + (px * q[1] - py * q[0])) + q[2] * cs;
-            const float nw = q[3] * cs - ((px * q[0] + py * q[1]) + pz * q[2]);
-            const float inv = 1.0f / sqrtf(((nx * nx + ny * ny) + nz * nz) + nw * nw);
+            const float dx = k * wb[0], dy = k * wb[1], dz = k * wb[2];
+            const float nx = fmaf(q[3], dx, fmaf(cs, q[0], fmaf(q[1], dz, -(q[2] * dy))));
+            const float ny = fmaf(q[3], dy, fmaf(cs, q[1], fmaf(q[2], dx, -(q[0] * dz))));
+            const float nz = fmaf(q[3], dz, fmaf(cs, q[2], fmaf(q[0], dy, -(q[1] * dx))));
+            const float nw = fmaf(q[3], cs, -fmaf(q[0], dx, fmaf(q[1], dy, q[2] * dz)));
+            const float s2 = fmaf(nx, nx, fmaf(ny, ny, fmaf(nz, nz, nw * nw)));
+            const float inv = fmaf(-0.5f, s2, 1.5f);
             q[0] = nx * inv; q[1] = ny * inv; q[2] = nz * inv; q[3] = nw * inv;
             quat_to_R(q, R);
+            if (s + 1 < d.nsub) mtv(R, tau_w, tb);
         }
+        mv(R, wb, w);
         for (int j = 0; j < 3; ++j) rc[j] = c->com_z * R[j][2];
         cross3(w, rc, t3);
         for (int j = 0; j < 3; ++j) { p[j] = x[j] - rc[j]; v[j] = v[j] - t3[j]; }

@@ -545,6 +545,7 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
     const double h = (double)c.dt / (double)c.substeps;
     d.h = (float)h;
     d.hh = (float)(0.5 * h);
+    d.hh2 = d.hh * d.hh;
     d.fault_eff_lo = c.fault_eff_lo; d.fault_eff_range = c.fault_eff_range;
     d.land_cutoff = c.land_cutoff;
     d.plate_enable = c.plate_enable; d.plate_z = c.plate_z;

@@ -178,7 +178,7 @@ extern "C" int ozl_quadcopter_step(const ozl_quadcopter_args* a, void* stream) {
     b.max_angvel2 = (float)((double)b.max_angvel * (double)b.max_angvel);
     b.gravity_z = a->gravity_z; b.lin_drag = 0.0f;
     const double h = (double)a->dt / (double)a->substeps;
-    b.h = (float)h; b.hh = (float)(0.5 * h);
+    b.h = (float)h; b.hh = (float)(0.5 * h); b.hh2 = b.hh * b.hh;
     b.sinc_c1 = (float)(-1.0 / 6.0); b.sinc_c2 = (float)(1.0 / 120.0);
     b.cos_c1 = -0.5f; b.cos_c2 = (float)(1.0 / 24.0); b.cos_c3 = (float)(-1.0 / 720.0);
     b.inv3 = 1.0f / 3.0f; b.half = 0.5f; b.inv_pi = 1.0f / (float)M_PI;
