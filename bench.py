@@ -29,6 +29,20 @@ if ROOT not in sys.path:
 ALG_BYTES_PER_ENV_STEP = 284          # reads 144 + writes 140
 WORKLOAD = "x500 trajectory tracking + single-rotor loss-of-effectiveness fault, 16384 envs per GPU (BASELINE configs[1])"
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
+SHARDS = 64                           # independent 16384-env shards the timed steps rotate over (64 x 4.9 MB = 314 MB > 126 MB L2)
+METRICS_EVERY = 16                    # BASELINE config 4: metrics vector read (+ NCCL all-reduce when N > 1) every 16 steps
+
+
+def config_of(envs_per_gpu, world):
+    """The `config` object, IDENTICAL in both arms (the reference arm runs on the GPU arm's config)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs_per_gpu, "envs_total": world * envs_per_gpu,
+            "mode": "A: actions read from HBM, obs/rew/reset/progress written to HBM",
+            "l2": f"inputs larger than L2: the K timed steps rotate over {SHARDS} independent {envs_per_gpu}-env shards "
+                  f"({SHARDS} x 4.9 MB = 314 MB > 126 MB L2) and the L2 is overwritten (256 MiB) between the warm-up replay and the "
+                  "timed replay, so every timed step starts cold at any K; K steps block-timed with one CUDA-event pair (CUDA graph replay) "
+                  "behind a GPU pre-roll that lets the host finish enqueueing before the first event fires",
+            "parallelism": f"env-sharded x{world}, no data-path collective; the 16-double metrics vector is read every {METRICS_EVERY} steps "
+                           "INSIDE the timed graph and, for N > 1, all-reduced with NCCL on a side stream inside the same graph"}
 
 
 def parse():
@@ -41,6 +55,7 @@ def parse():
     p.add_argument("--roofline-envs", type=int, default=1 << 20)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-side-configs", action="store_true")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--roofline-only", action="store_true", help="profiling aid: run only the 1 Mi-env roofline region")
     return p.parse_args()
@@ -88,7 +103,7 @@ class ClockSampler:
                             self.reasons.add(name)
                 except Exception:  # noqa: BLE001
                     pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def start(self):
         if self.ok:
@@ -191,10 +206,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": sample,
-                   "note": "CPU restatement of the reference step (PhysX unavailable): C port of the oracle, OpenMP over envs, all host threads"},
+        "config": config_of(args.envs, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} envs of the workload (host cores only)"},
+                         "sample": f"{args.steps} steps x {sample} envs of the workload (host cores only; the whole-job workload is {n} envs per step)",
+                         "note": "CPU restatement of the reference step (PhysX unavailable): C port of the oracle, OpenMP over envs, all host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,11 +267,15 @@ def run_ours(args):
     clocks.start()
     if args.roofline_only:
         K, W = 1, 1
-        args.no_e2e = args.no_cpu_baseline = True
+        args.no_e2e = args.no_cpu_baseline = args.no_side_configs = True
 
-    # ---- headline: EXACTLY K steps, block-timed; every step's inputs are cold because the steps rotate over S independent
-    #      16384-env shards whose combined footprint (S x 4.9 MB) exceeds the 126 MB L2 ("inputs larger than L2") --------------
-    S = 64
+    # ---- headline: EXACTLY K steps, block-timed; every step's inputs are cold because (a) the steps rotate over S independent
+    #      16384-env shards whose combined footprint (S x 4.9 MB) exceeds the 126 MB L2 and (b) the L2 is overwritten between the
+    #      warm-up replay and the timed replay (K < S would otherwise re-touch warm shards).  The metrics vector is read every 16
+    #      steps inside the graph and, for N > 1, all-reduced with NCCL on a side stream inside the same graph (config 4's only
+    #      collective).  A ~0.4 ms GPU pre-roll sits in front of the first event so the host has enqueued every graph launch
+    #      before the timed region begins: the event pair sees device time only, no host launch gaps.
+    S = SHARDS
     shards = [(sim, obs, rew, reset, prog, tout, epr)]
     # one allocation per buffer kind, sliced per shard (keeps the ncu launch list free of hundreds of fill kernels)
     b_obs, b_rew, b_epr = torch.zeros(S, n, 13, device=dev), torch.zeros(S, n, device=dev), torch.zeros(S, n, device=dev)
@@ -265,31 +284,68 @@ def run_ours(args):
     for j in range(1, S):
         shards.append((QuadSim(_lib.default_cfg(n, seed=args.seed + j, env_id_base=(rank * S + j) * n, **task_cfg_kwargs()), dev),
                        b_obs[j], b_rew[j], b_rst[j], b_prog[j], b_tout[j], b_epr[j]))
+    n_reads = (K + METRICS_EVERY - 1) // METRICS_EVERY + 1
+    metrics_ring = torch.zeros(n_reads, 16, dtype=torch.float64, device=dev)
+    nccl_in_graph = world > 1
 
     def step_rot(k):
         sm, o_, r_, rs_, pg_, to_, er_ = shards[k % S]
         sm.step(pool[k & 7], o_, r_, rs_, pg_, to_, er_)
 
+    def metrics_in_graph(k, with_nccl):
+        # one metrics_read kernel on the step stream; the all-reduce forks to the side stream and joins at the end of the capture
+        m = metrics_ring[(k // METRICS_EVERY) % n_reads]
+        shards[k % S][0].metrics(clear=False, out=m)
+        if with_nccl:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_reduce(m, op=dist.ReduceOp.SUM)
+
     for k in range(max(W, S)):
         step_rot(k)
-    def graph_of(step_fn, count):
+
+    def graph_of(step_fn, count, k0=0, extra=None):
         g_ = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g_):
-            for k in range(count):
+        with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+            for k in range(k0, k0 + count):
                 step_fn(k)
+                if extra is not None and (k % METRICS_EVERY) == METRICS_EVERY - 1:
+                    extra(k)
+            if extra is not None:
+                torch.cuda.current_stream().wait_stream(side)     # join the side stream (no-op when nothing forked)
         return g_
 
     chunk_r = K if K <= 512 else 512
     reps_r, rem_r = K // chunk_r, K % chunk_r
-    gr_rot = graph_of(step_rot, chunk_r)
-    gr_rot_rem = graph_of(step_rot, rem_r) if rem_r else None       # the remainder is graph-launched too: EXACTLY K steps, no eager launches
-    gr_rot.replay()
+
+    def build_headline(with_nccl):
+        ex = (lambda k: metrics_in_graph(k, with_nccl))
+        g1 = graph_of(step_rot, chunk_r, 0, ex)
+        g2 = graph_of(step_rot, rem_r, reps_r * chunk_r, ex) if rem_r else None    # the remainder is graph-launched too: EXACTLY K steps
+        return g1, g2
+    try:
+        gr_rot, gr_rot_rem = build_headline(nccl_in_graph)
+    except Exception as e:  # noqa: BLE001  -- NCCL capture refused on this stack: keep the metrics read, drop the in-graph all-reduce
+        sys.stderr.write(f"[bench] rank {rank}: NCCL all-reduce could not be captured ({e!r}); timing without it\n")
+        nccl_in_graph = False
+        torch.cuda.synchronize()
+        gr_rot, gr_rot_rem = build_headline(False)
+    if world > 1:      # every rank must agree on what was captured
+        flag = torch.tensor([1 if nccl_in_graph else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and nccl_in_graph:
+            nccl_in_graph = False
+            gr_rot, gr_rot_rem = build_headline(False)
+    n_metric_reads = sum(1 for k in range(K) if (k % METRICS_EVERY) == METRICS_EVERY - 1)
+    clocks.region(True)          # NVML sampling (1 ms period) runs from here to the end of the warm-L2 region: the timed replay alone
+    gr_rot.replay()              # (K x ~4 us) is shorter than one NVML query, so the window also covers the warm-up replays around it
     if gr_rot_rem is not None:
         gr_rot_rem.replay()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.region(True)
+    flush.zero_()                                   # overwrite the L2: the warm-up replay touched the same shards the timed one will
+    torch.cuda._sleep(800_000)                      # ~0.4 ms spin kernel: the host enqueues everything below while it runs
     e0.record()
     for _ in range(reps_r):
         gr_rot.replay()
@@ -297,9 +353,12 @@ def run_ours(args):
         gr_rot_rem.replay()
     e1.record()
     barrier()
-    clocks.region(False)
     tr = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    per_rank_ms = [float(tr.item())]
     if world > 1:
+        gathered = [torch.zeros_like(tr) for _ in range(world)]
+        dist.all_gather(gathered, tr)
+        per_rank_ms = [float(t_.item()) for t_ in gathered]
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
     rot_ms = float(tr.item())
     value_rot = world * n * K / (rot_ms * 1e-3)
@@ -312,7 +371,6 @@ def run_ours(args):
         step(k)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
-    clocks.region(True)
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
@@ -321,7 +379,6 @@ def run_ours(args):
         if (k & 15) == 15:
             metrics_allreduce()
     barrier()
-    clocks.region(False)
     ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -341,7 +398,7 @@ def run_ours(args):
         gr_rem.replay()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.region(True)
+    torch.cuda._sleep(800_000)
     e0.record()
     for _ in range(reps):
         gr.replay()
@@ -522,18 +579,37 @@ def run_ours(args):
                "sample": f"{steps_c} steps x {envs_c} envs (C restatement of the reference step, OpenMP over envs; PhysX unavailable)",
                "torch_eager_port": {"value": vt, "sample": f"{steps_t} steps x {envs_t} envs (torch-CPU eager restatement, the reference's own op-by-op style)"}}
 
+    # ---- the other BASELINE configs, driver-visible (configs 1 and 3 on one GPU; config 5 on every rank, max over ranks) -------
+    side_configs = None
+    if not args.no_side_configs:
+        try:
+            from benchmarks import configs as side
+            side_configs = {}
+            torch.cuda.set_device(local)
+            c5 = side.config5(str(dev), iters=8)
+            if rank == 0:
+                side_configs["config5_rpo_lstm_rollout_collection"] = c5
+            if world == 1:
+                side_configs["config1_quadcopter_hover_256"] = side.config1(str(dev))
+                side_configs["config3_ekf_pv_lee_65536"] = side.config3(str(dev), steps=100)
+        except Exception as e:  # noqa: BLE001 -- a side line must never take the headline down
+            side_configs = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": rot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs_total": world * n, "mode": "A: actions read from HBM, obs/rew/reset/progress written to HBM",
-                       "l2": "inputs larger than L2: the K timed steps rotate over 64 independent 16384-env shards (64 x 4.9 MB = 314 MB > 126 MB L2), so every step starts cold; K steps block-timed with one CUDA-event pair (CUDA graph replay)",
-                       "parallelism": f"env-sharded x{world}, no data-path collective; the 16-double metrics all-reduce (NCCL, side stream, every 16 steps) runs inside the value_flush_per_step_events region"},
+            "config": config_of(n, world),
+            "ms_per_rank": per_rank_ms,
+            "metrics_reads_in_timed_graph": n_metric_reads, "nccl_allreduce_in_timed_graph": bool(nccl_in_graph),
             "value_flush_per_step_events": value_flush, "ms_per_step_flush_per_step_events": ms / K,
             "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms / K,
             "clocks": clocks.result(),
-            "e2e": e2e, "gpu_launches": K,
+            "e2e": e2e, "gpu_launches": K + n_metric_reads,
+            "gpu_launches_note": f"{K} quad_step_kernel<128> + {n_metric_reads} metrics_read_kernel per rank inside the timed region"
+                                 + (f" (+ {n_metric_reads} NCCL all-reduce kernels, library)" if nccl_in_graph else ""),
+            "side_configs": side_configs,
             "roofline": roofline, "roofline_at_workload": roofline_wl,
             "cpu_baseline": cpu,
         }

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 # (they hard-code "cuda:0").  Must happen before torch initialises CUDA.
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 RANK = int(os.environ.get("RANK", "0"))
-if WORLD > 1:
+if WORLD > 1 and __name__ == "__main__":       # (bench.py imports this module for its `side_configs` and addresses GPUs by local rank)
     os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("LOCAL_RANK", "0")
 import torch  # noqa: E402
 
@@ -41,7 +41,7 @@ def timed(fn, steps, warmup):
     return e0.elapsed_time(e1) * 1e-3
 
 
-def config1():
+def config1(DEV=DEV):
     n, steps = 256, 1000
     env = ouzelum_b200.make(seed=0, task="Quadcopter", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True)
     g = torch.Generator().manual_seed(0)
@@ -87,8 +87,8 @@ def config1():
             "cpu_note": "torch-CPU eager oracle of the same step (Isaac Gym CPU pipeline unavailable)"}
 
 
-def config3():
-    n, steps = 65536, 200
+def config3(DEV=DEV, steps=200):
+    n = 65536
     cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=0, POMDP="random_noise", pomdp_prob=0.15, ConvergenceTime=20,
                                    domainRandomization={"enable": True}, rotorFault={"enable": True}, useCudaGraph=True)
     env = ouzelum_b200.make(seed=0, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
@@ -102,7 +102,8 @@ def config3():
     alg = 1372
     return {"config": 3, "workload": "x500 + DR + sensor noise sigma 0.15 + EKF (f64) + PV filter (full 9x9) + Lee controller, 65536 envs",
             "env_steps_per_sec": n * steps / dt, "us_per_step": dt / steps * 1e6, "alg_bytes_per_env_step": alg,
-            "achieved_GBps_alg": alg * n * steps / dt / 1e9, "launches_per_step": 1,
+            "achieved_GBps_alg": alg * n * steps / dt / 1e9, "frac_of_hbm_peak": alg * n * steps / dt / 1e9 / 6552.3,
+            "launches_per_step": 1,
             "per_env_sensor_triggers_env_steps_per_sec": n * steps / dt2,
             "landings": env.landings, "episodes": env.episodes}
 
@@ -129,7 +130,7 @@ def config4():
     return {"config": 4, "workload": "x500 rotor-fault step at the per-GPU shard sizes of the 1 Mi-env job (and 4 Mi)", "sizes": out}
 
 
-def config5():
+def config5(DEV=DEV, iters=20):
     from ouzelum_b200.pomdp import POMDPWrapper
     from ouzelum_b200.rollout import RecurrentActor, RolloutStorage, collect_rollout, initial_rollout_state
     n, T = 32768, 16
@@ -142,7 +143,6 @@ def config5():
 
     def f():
         st[0] = collect_rollout(env, actor, store, st[0], pomdp)
-    iters = 20
     dt_fp32 = timed(f, iters, 3)
     torch.backends.cuda.matmul.allow_tf32 = True          # the policy GEMMs on tensor cores (TF32); the env kernels are unaffected
     dt = timed(f, iters, 3)
