@@ -292,6 +292,8 @@ def run_ours(args):
         sm, o_, r_, rs_, pg_, to_, er_ = shards[k % S]
         sm.step(pool[k & 7], o_, r_, rs_, pg_, to_, er_)
 
+    forked = [False]
+
     def metrics_in_graph(k, with_nccl):
         # one metrics_read kernel on the step stream; the all-reduce forks to the side stream and joins at the end of the capture
         m = metrics_ring[(k // METRICS_EVERY) % n_reads]
@@ -300,6 +302,7 @@ def run_ours(args):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 dist.all_reduce(m, op=dist.ReduceOp.SUM)
+            forked[0] = True
 
     for k in range(max(W, S)):
         step_rot(k)
@@ -307,13 +310,15 @@ def run_ours(args):
     def graph_of(step_fn, count, k0=0, extra=None):
         g_ = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        forked[0] = False
         with torch.cuda.graph(g_, capture_error_mode="thread_local"):
             for k in range(k0, k0 + count):
                 step_fn(k)
                 if extra is not None and (k % METRICS_EVERY) == METRICS_EVERY - 1:
                     extra(k)
-            if extra is not None:
-                torch.cuda.current_stream().wait_stream(side)     # join the side stream (no-op when nothing forked)
+            if forked[0]:
+                torch.cuda.current_stream().wait_stream(side)     # join the side stream the all-reduces were forked to
+                forked[0] = False
         return g_
 
     chunk_r = K if K <= 512 else 512

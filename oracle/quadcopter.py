@@ -48,7 +48,7 @@ def compute_observations(root_states, dof_positions):
 import numpy as np  # noqa: E402
 
 from . import philox as px  # noqa: E402
-from .quad_step import QuadStepOracle, default_cfg  # noqa: E402
+from .quad_step import QuadStepOracle, _cross, default_cfg  # noqa: E402
 
 
 def vehicle_constants():
@@ -140,7 +140,7 @@ class QuadcopterOracle:
             d = [ca * dl[0] - sa * dl[1], sa * dl[0] + ca * dl[1], dl[2]]
             p = [ca * pl[0] - sa * pl[1], sa * pl[0] + ca * pl[1], pl[2]]
             f = [force[:, k] * d[j] for j in range(3)]
-            t3 = [p[1] * f[2] - p[2] * f[1], p[2] * f[0] - p[0] * f[2], p[0] * f[1] - p[1] * f[0]]
+            t3 = _cross(p, f)                                   # same fused form as cross3() in quad_env.cuh
             fb = [fb[j] + f[j] for j in range(3)]
             tau = [tau[j] + t3[j] for j in range(3)]
         b.root = self.root
