@@ -31,6 +31,7 @@ WORKLOAD = "x500 trajectory tracking + single-rotor loss-of-effectiveness fault,
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
 SHARDS = 64                           # independent 16384-env shards the timed steps rotate over (64 x 4.9 MB = 314 MB > 126 MB L2)
 METRICS_EVERY = 16                    # BASELINE config 4: metrics vector read (+ NCCL all-reduce when N > 1) every 16 steps
+METRICS_PHASE = 7                     # ... after steps 7, 23, 39, ...: the asynchronous all-reduce has the following steps to hide behind
 
 
 def config_of(envs_per_gpu, world):
@@ -314,7 +315,7 @@ def run_ours(args):
         with torch.cuda.graph(g_, capture_error_mode="thread_local"):
             for k in range(k0, k0 + count):
                 step_fn(k)
-                if extra is not None and (k % METRICS_EVERY) == METRICS_EVERY - 1:
+                if extra is not None and (k % METRICS_EVERY) == METRICS_PHASE:
                     extra(k)
             if forked[0]:
                 torch.cuda.current_stream().wait_stream(side)     # join the side stream the all-reduces were forked to
@@ -342,7 +343,7 @@ def run_ours(args):
         if int(flag.item()) == 0 and nccl_in_graph:
             nccl_in_graph = False
             gr_rot, gr_rot_rem = build_headline(False)
-    n_metric_reads = sum(1 for k in range(K) if (k % METRICS_EVERY) == METRICS_EVERY - 1)
+    n_metric_reads = sum(1 for k in range(K) if (k % METRICS_EVERY) == METRICS_PHASE)
     clocks.region(True)          # NVML sampling (1 ms period) runs from here to the end of the warm-L2 region: the timed replay alone
     gr_rot.replay()              # (K x ~4 us) is shorter than one NVML query, so the window also covers the warm-up replays around it
     if gr_rot_rem is not None:

@@ -45,29 +45,20 @@ struct PVArgs {
     uint64_t iter_base;                                        // global iteration index of env 0 (tasks/ekf_lee_landed.py:425-440)
 };
 
-__device__ __forceinline__ void pv_load(const PVArgs& a, int64_t i, PV& s) {
+// Stand-alone PV filter step: the block's [81][128] covariance slice is staged in shared memory (coalesced plane loads) and the
+// filter runs on it with the same device functions as the fused EKFLeeLanded kernel (filters.cuh) -- identical bits.
+constexpr int kPvBlock = 128;
+__global__ void __launch_bounds__(kPvBlock)
+pv_step_kernel(const PVArgs a) {
+    __shared__ float s_P[81 * kPvBlock];
+    const int64_t i = (int64_t)blockIdx.x * kPvBlock + threadIdx.x;
+    if (i >= a.n) return;                              // no block-level synchronisation below: every thread works on its own column
+    PVShared<kPvBlock> s;
+    s.P = s_P + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 9; ++k) s.x[k] = a.x[(int64_t)k * a.n + i];
-#pragma unroll
-    for (int r = 0; r < 9; ++r)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) s.P[r][c] = a.P[(int64_t)(r * 9 + c) * a.n + i];
-}
-__device__ __forceinline__ void pv_store(const PVArgs& a, int64_t i, const PV& s) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) a.x[(int64_t)k * a.n + i] = s.x[k];
-#pragma unroll
-    for (int r = 0; r < 9; ++r)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) a.P[(int64_t)(r * 9 + c) * a.n + i] = s.P[r][c];
-}
-
-__global__ void __launch_bounds__(128)
-pv_step_kernel(const PVArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    PV s;
-    pv_load(a, i, s);
+#pragma unroll 9
+    for (int k = 0; k < 81; ++k) s_P[k * kPvBlock + threadIdx.x] = a.P[(int64_t)k * a.n + i];
     if (a.do_predict) {
         const float acc[3] = {a.accel[i * 3], a.accel[i * 3 + 1], a.accel[i * 3 + 2]};
         const float4 q4 = reinterpret_cast<const float4*>(a.quat)[i];
@@ -88,7 +79,10 @@ pv_step_kernel(const PVArgs a) {
         const float z[3] = {a.vel_meas[i * 3], a.vel_meas[i * 3 + 1], a.vel_meas[i * 3 + 2]};
         pv_correct<3>(s, z, a.vel_var);
     }
-    pv_store(a, i, s);
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) a.x[(int64_t)kk * a.n + i] = s.x[kk];
+#pragma unroll 9
+    for (int kk = 0; kk < 81; ++kk) a.P[(int64_t)kk * a.n + i] = s_P[kk * kPvBlock + threadIdx.x];
 }
 
 __global__ void pv_init_kernel(int64_t n, float* x, float* P) {
