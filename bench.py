@@ -489,8 +489,8 @@ def run_ours(args):
             eh.close()
         e2e = {"value": v_host, "unit": UNIT,
                "h2d_bytes_per_step": world * h_act[0].numel() * 4,
-               "d2h_bytes_per_step": world * (n * 13 * 4 + n * 4 + n),
-               "api": "ouzelum_b200.make(...).step_host(pinned actions) -> pinned (obs, reward, done): one launch, zero-copy PCIe reads/writes inside the kernel, stream sync",
+               "d2h_bytes_per_step": world * (n * 13 * 4 + n * 4 + n * 8 + n),
+               "api": "ouzelum_b200.make(...).step_host(pinned actions) -> pinned (obs f32 [N,13], reward f32 [N], reset int64 [N]; + the same flags as u8): one launch, zero-copy PCIe reads/writes inside the kernel, stream sync",
                "value_pipelined_two_halves": v_halves,
                "pipelined_two_halves": "two task objects of n/2 envs on two streams, step_host_async / step_host_wait: one half's PCIe write-back overlaps the other half's step (for consumers that can work on halves; not the reference's synchronous step)",
                "value_with_explicit_copies": v_copy,

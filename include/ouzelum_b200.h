@@ -26,10 +26,33 @@
 extern "C" {
 #endif
 
-#define OZL_ABI_VERSION 2   /* 2: ozl_quadcopter_args.step_record, step-counter record layout (ozl_step_counter_ptr), ozl_host_io */
+#define OZL_ABI_VERSION 3   /* 3: ozl_cfg.dr[] (domain-randomisation schema), per-env yaw_km (params8), wrench_warmup_steps,
+                               ozl_ekf_lee_args.num_envs_total, i64 reset mirror in ozl_host_io */
 
 /* sensor-fault model of isaacgymenvs/utils/POMDP.py:4-42 */
 enum { OZL_POMDP_NONE = 0, OZL_POMDP_FLICKER = 1, OZL_POMDP_NOISE = 2, OZL_POMDP_FLICKER_NOISE = 3 };
+
+/* Domain randomisation of one per-env parameter, drawn when the env is reset.  Schema of the reference's
+ * `randomization_params` (isaacgymenvs/utils/dr_utils.py:71-132 generate_random_samples, applied at resets only,
+ * tasks/base/vec_task.py:538-768):
+ *   distribution  uniform: range = (lo, hi) ; loguniform: exp(U(log lo, log hi)) ; gaussian: range = (mu, sigma)
+ *   operation     scaling: param = nominal * sample ; additive: param = nominal + sample
+ *   schedule      none ; linear: s = min(step, schedule_steps) / schedule_steps ; constant: s = step < schedule_steps ? 0 : 1
+ *                 additive: range *= s ; scaling: lo/hi/mu -> x*s + (1-s), sigma -> sigma*s     (dr_utils.py:82-131)
+ * `step` is the handle's step counter (the reference's gym frame count).  Draws are Philox words keyed by (seed, global env id,
+ * step): word j of P_DR0|P_DR1 for parameter j (and word j of P_DR2|P_DR3 as the second uniform of a gaussian). */
+enum { OZL_DR_NONE = 0, OZL_DR_UNIFORM = 1, OZL_DR_LOGUNIFORM = 2, OZL_DR_GAUSSIAN = 3 };
+enum { OZL_DR_SCALING = 0, OZL_DR_ADDITIVE = 1 };
+enum { OZL_DR_SCHED_NONE = 0, OZL_DR_SCHED_LINEAR = 1, OZL_DR_SCHED_CONSTANT = 2 };
+enum { OZL_DR_MASS = 0, OZL_DR_IXX = 1, OZL_DR_IYY = 2, OZL_DR_IZZ = 3, OZL_DR_ARM = 4, OZL_DR_THRUST_SCALE = 5, OZL_DR_YAW_KM = 6,
+       OZL_DR_NUM = 7 };
+typedef struct ozl_dr_param {
+    int32_t distribution;         /* OZL_DR_NONE / _UNIFORM / _LOGUNIFORM / _GAUSSIAN */
+    int32_t operation;            /* OZL_DR_SCALING / _ADDITIVE */
+    float range[2];               /* (lo, hi) or (mu, sigma) */
+    int32_t schedule;             /* OZL_DR_SCHED_* */
+    int32_t schedule_steps;
+} ozl_dr_param;
 
 /* Task configuration.  Defaults (ozl_cfg_default) reproduce isaacgymenvs/cfg/task/Ouzelum.yaml and
  * the literals in isaacgymenvs/tasks/ouzelum.py; the "extras" are zero-default options with no
@@ -66,8 +89,9 @@ typedef struct ozl_cfg {
     float yaw_km;                 /* rotor reaction torque about body z per newton of thrust                      */
     int32_t fault_mode;           /* 1: single-rotor loss of effectiveness, schedule drawn at reset               */
     float fault_eff_lo, fault_eff_range;
-    int32_t dr_enable;            /* 1: mass/Ixx/Iyy/Izz/arm/thrust-scale *= U[dr_lo, dr_lo+dr_range) at reset    */
-    float dr_lo, dr_range;        /*    (schema of isaacgymenvs/utils/dr_utils.py:121-130: scaling, uniform)      */
+    int32_t dr_enable;            /* 1: randomise the per-env parameters at reset according to dr[]               */
+    ozl_dr_param dr[7];           /* indexed by OZL_DR_*; default: mass/Ixx/Iyy/Izz/arm/thrust-scale = scaling x uniform
+                                     [0.8, 1.2) (dr_utils.py:121-130), yaw_km = none                              */
     int32_t pomdp_mode;           /* OZL_POMDP_* applied to the observation inside the step (tasks/landed.py:340) */
     float pomdp_prob;             /* flicker probability                                          POMDP.py:8      */
     float noise_sigma;            /* multiplicative noise U(1-s, 1+s)                             POMDP.py:9-10   */
@@ -77,6 +101,10 @@ typedef struct ozl_cfg {
     float plate_radius;           /* horizontal reach of the plate around the target                              */
     float land_cutoff;            /* >0: zero the wrench within this distance of the target and flag a landing
                                      (tasks/landed.py:288-295 0.2, lee_landed.py:318-322 0.2, ekf_lee_landed.py:508-515 0.25) */
+    int32_t wrench_warmup_steps;  /* wrench-actuated steps with step counter < this value are the estimator warm-up of
+                                     tasks/ekf_lee_landed.py:339,508-529: the wrench reaches EVERY env (no near-target cut, no
+                                     zeroing for just-reset envs) and the landing flag is not raised.  0 = no warm-up      */
+    int32_t reserved1;
 } ozl_cfg;
 
 typedef struct ozl_env ozl_env;   /* opaque */
@@ -122,6 +150,7 @@ typedef struct ozl_host_io {
     float* obs_host;            /* [N,13] pinned */
     float* rew_host;            /* [N] pinned */
     uint8_t* done_host;         /* [N] pinned */
+    int64_t* reset_host;        /* [N] pinned or NULL: reset_buf mirrored with the reference's dtype (vec_task.py:353-359) */
     int64_t* reset;             /* [N] device */
     int64_t* progress;          /* [N] device */
     uint8_t* timeout;           /* [N] device or NULL */
@@ -161,10 +190,11 @@ int ozl_rollout(ozl_env* env, int32_t K, float* obs, float* rew, int64_t* reset,
 int ozl_get_state(ozl_env* env, float* root13, float* thrust4, float* target3, float* ep_ret, void* stream);
 int ozl_set_state(ozl_env* env, const float* root13, const float* thrust4, const float* target3,
                   const float* ep_ret, void* stream);
-/* per-env parameters: params7 [N,7] = mass, ixx, iyy, izz, arm, thrust_scale, fault_effectiveness;
- * fault2 [N,2] i32 = fault rotor id, fault onset step (0x1FFFFFFF: never). */
-int ozl_get_params(ozl_env* env, float* params7, int32_t* fault2, void* stream);
-int ozl_set_params(ozl_env* env, const float* params7, const int32_t* fault2, void* stream);
+/* per-env parameters: params8 [N,8] = mass, ixx, iyy, izz, arm, thrust_scale, fault_effectiveness, yaw_km;
+ * fault2 [N,2] i32 = fault rotor id, fault onset step (0x1FFFFFFF: never), landed flag in bit 31 of the onset word.
+ * Mass and inertia must be positive normal floats (the step evaluates their IEEE reciprocals on a range-checked fast path). */
+int ozl_get_params(ozl_env* env, float* params8, int32_t* fault2, void* stream);
+int ozl_set_params(ozl_env* env, const float* params8, const int32_t* fault2, void* stream);
 
 /* Step counter (the RNG's time axis): number of ozl_step's since ozl_reset_all.  Host-synchronising. */
 int ozl_get_step_count(ozl_env* env, uint64_t* out, void* stream);
@@ -270,6 +300,8 @@ typedef struct ozl_ekf_lee_args {
     float pomdp_prob;
     uint32_t pos_period, pos_phase, vel_period, vel_phase;   /* (7,6,3,0) for 20 / 75 Hz at dt 0.01 */
     int32_t per_env_triggers; /* 0: the reference's counters shared by all envs; 1: every env counts its own steps */
+    int64_t num_envs_total;   /* envs of the WHOLE job (all ranks); 0 = this handle's.  The shared counters advance once per
+                                 env-iteration, so fix k of env e at step t is t * num_envs_total + global id(e): invariant to sharding */
     float acc_var[3], pos_var[3];
     double ekf_Dt, ekf_g_noise;
 } ozl_ekf_lee_args;
@@ -337,6 +369,24 @@ typedef struct ozl_husky_args {
 } ozl_husky_args;
 int ozl_husky_init(const ozl_husky_args* args, void* stream);
 int ozl_husky_step(const ozl_husky_args* args, void* stream);
+
+/* Landing / Landed in ONE launch: the vehicle step (ozl_husky_step) and the tracking step (ozl_step_tracking) per env in one
+ * thread.  Replaces VecTask.step for isaacgymenvs/tasks/landing.py (set_husky_actions :319-364, target rule :373-374,
+ * pre/post_physics_step) and landed.py.  `husky` follows the handle's device step counter (`step` / `step_ptr` ignored). */
+int ozl_landing_step(ozl_env* env, const float* actions, const ozl_husky_args* husky, float* obs, float* rew, int64_t* reset,
+                     int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
+
+/* LeeLanded in ONE launch (isaacgymenvs/tasks/lee_landed.py:263-330): vehicle, Lee position controller on the true state after
+ * reset_idx towards the fixed command `cmd` (:299-302, (0,0,1,yaw 0)), wrench = (mg * thrust, torque) on the base link (:313-314),
+ * landing detector on the CONTROLLER target within cfg.land_cutoff (:305,318-322), physics / observation / reward / reset. */
+typedef struct ozl_lee_landed_args {
+    const float* gains16;     /* HOST: kP, kV, kR, kOmega, scale_input   (controllers/control_config.py:13-18) */
+    float cmd[4];             /* controller target x, y, z, yaw */
+    float mg;                 /* 2 * 9.81   lee_landed.py:296 */
+    float* wrench4;           /* [N,4] out or NULL: the wrench the controller asked for (before the landing / reset zeroing) */
+} ozl_lee_landed_args;
+int ozl_lee_landed_step(ozl_env* env, const ozl_lee_landed_args* args, const ozl_husky_args* husky, float* obs, float* rew,
+                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream);
 
 /* Stock Quadcopter hover task (BASELINE config 1): one fused step.  Replaces VecTask.step with the hooks of
  * isaacgymenvs/tasks/quadcopter.py:280-330,359-418.  All state is caller-owned AoS device memory:

@@ -37,6 +37,11 @@ def build(force=False):
     return OUT
 
 
+class OracleDrParam(C.Structure):
+    _fields_ = [("distribution", C.c_int32), ("operation", C.c_int32), ("range", C.c_float * 2),
+                ("schedule", C.c_int32), ("schedule_steps", C.c_int32)]
+
+
 class OracleCfg(C.Structure):
     """Independent mirror of `struct ozl_cfg` (include/ouzelum_b200.h) so that the CPU arm needs nothing from the product."""
     _fields_ = [
@@ -53,10 +58,10 @@ class OracleCfg(C.Structure):
         ("arm", C.c_float), ("com_z", C.c_float), ("max_angvel", C.c_float),
         ("lin_drag", C.c_float), ("yaw_km", C.c_float),
         ("fault_mode", C.c_int32), ("fault_eff_lo", C.c_float), ("fault_eff_range", C.c_float),
-        ("dr_enable", C.c_int32), ("dr_lo", C.c_float), ("dr_range", C.c_float),
+        ("dr_enable", C.c_int32), ("dr", OracleDrParam * 7),
         ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float), ("noise_sigma", C.c_float),
         ("collect_metrics", C.c_int32), ("plate_enable", C.c_int32), ("plate_z", C.c_float), ("plate_radius", C.c_float),
-        ("land_cutoff", C.c_float),
+        ("land_cutoff", C.c_float), ("wrench_warmup_steps", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -67,11 +72,16 @@ def make_cfg(cfg_dict):
     for k, v in cfg_dict.items():
         if k not in names:
             continue
-        if isinstance(v, (tuple, list)):
+        if k == "dr":
+            for j, spec in enumerate(v):
+                d = c.dr[j]
+                d.distribution, d.operation, d.schedule, d.schedule_steps = int(spec[0]), int(spec[1]), int(spec[4]), int(spec[5])
+                d.range[0], d.range[1] = float(spec[2]), float(spec[3])
+        elif isinstance(v, (tuple, list)):
             getattr(c, k)[:] = [float(x) for x in v]
         else:
             setattr(c, k, v)
-    c.abi_version = 1
+    c.abi_version = 3
     return c
 
 
@@ -93,8 +103,8 @@ class COracle:
         self.root[:, 6] = 1
         self.thrust, self.target, self.ep_ret = np.zeros((n, 4), f), np.zeros((n, 3), f), np.zeros(n, f)
         self.target[:, 2] = 1
-        self.params = np.zeros((n, 7), f)
-        self.params[:] = [cfg_struct.mass, cfg_struct.ixx, cfg_struct.iyy, cfg_struct.izz, cfg_struct.arm, 1.0, 1.0]
+        self.params = np.zeros((n, 8), f)     # mass, ixx, iyy, izz, arm, thrust scale, fault effectiveness, yaw_km
+        self.params[:] = [cfg_struct.mass, cfg_struct.ixx, cfg_struct.iyy, cfg_struct.izz, cfg_struct.arm, 1.0, 1.0, cfg_struct.yaw_km]
         self.fault = np.zeros((n, 2), np.int32)
         self.fault[:, 1] = 0x1FFFFFFF
         self.obs_buf, self.rew_buf = np.zeros((n, 13), f), np.zeros(n, f)

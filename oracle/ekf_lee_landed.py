@@ -39,7 +39,7 @@ def _fault(x, mode, prob, seed, ids, step, stream, per_env_flicker):
 
 class EKFLeeGlue:
     def __init__(self, n, dt=0.01, convergence=300, pomdp_mode=0, pomdp_prob=0.0, seed=0, env_id_base=0, gravity_z=-9.81,
-                 trigger=(7, 6, 3, 0), per_env_triggers=False):
+                 trigger=(7, 6, 3, 0), per_env_triggers=False, n_total=None):
         f = np.float32
         self.n, self.dt, self.conv = n, f(dt), convergence
         self.mode, self.prob, self.seed = pomdp_mode, pomdp_prob, seed
@@ -55,6 +55,7 @@ class EKFLeeGlue:
         self.hover = f(-2.09 * gravity_z)
         self.trigger = trigger
         self.per_env = per_env_triggers      # True: every env counts its own steps instead of the reference's shared counters
+        self.n_total = int(n_total or n)     # envs of the whole job: the shared counters advance once per env-iteration
 
     def pre_physics(self, root, target, reset):
         """root [N,13] f32 AFTER reset_idx, target [N,3], reset [N] bool -> (wrench [N,4], est [N,13], cmd [N,4])."""
@@ -78,7 +79,7 @@ class EKFLeeGlue:
         self.pv.state[reset, 0:3], self.pv.state[reset, 3:6], self.pv.state[reset, 6:9] = pos[reset], vel[reset], 0
         orient = quat if warm else self.Q.astype(f)
         self.pv.prediction_step(acc_m, orient, self.dt, flip_Qw=warm)
-        k = np.full(n, t) if self.per_env else t * n + np.arange(n)
+        k = np.full(n, t) if self.per_env else t * self.n_total + self.ids.astype(np.int64)
         pp, ph, vp, vh = self.trigger
         var = np.full(3, 0.0000001, f)
         if pp:

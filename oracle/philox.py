@@ -20,7 +20,9 @@ P_TARGET = 0      # r0,r1 -> target x,y ; r2 -> target z
 P_SPAWN = 1       # r0,r1,r2 -> spawn x,y,z offsets
 P_FAULT = 2       # r0 -> rotor id ; r1 -> onset step ; r2 -> effectiveness
 P_DR0 = 3         # r0..r3 -> mass, Ixx, Iyy, Izz scalings
-P_DR1 = 4         # r0,r1 -> arm, thrust-scale scalings
+P_DR1 = 4         # r0,r1,r2 -> arm, thrust-scale, yaw_km
+P_DR2 = 24        # second uniforms of gaussian draws (mass, Ixx, Iyy, Izz)
+P_DR3 = 25        #                                   (arm, thrust-scale, yaw_km)
 P_QDOF0 = 5       # Quadcopter task: initial DOF positions 0..3
 P_QDOF1 = 6       #                  initial DOF positions 4..7
 P_OBSNOISE = 8    # +0..+3 : 13 per-element sensor-noise uniforms

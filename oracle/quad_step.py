@@ -40,6 +40,9 @@ from . import philox as px
 from . import x500
 
 POMDP_NONE, POMDP_FLICKER, POMDP_NOISE, POMDP_FLICKER_NOISE = 0, 1, 2, 3
+DR_NONE, DR_UNIFORM, DR_LOGUNIFORM, DR_GAUSSIAN = 0, 1, 2, 3
+DR_SCALING, DR_ADDITIVE = 0, 1
+DR_SCHED_NONE, DR_SCHED_LINEAR, DR_SCHED_CONSTANT = 0, 1, 2
 
 
 def default_cfg(num_envs, **over):
@@ -63,7 +66,11 @@ def default_cfg(num_envs, **over):
         max_angvel=x500.MAX_ANGVEL,
         lin_drag=0.0, yaw_km=0.0,            # north-star extras, zero => reference behaviour
         fault_mode=0, fault_eff_lo=0.0, fault_eff_range=0.5,
-        dr_enable=0, dr_lo=0.8, dr_range=1.2 - 0.8,
+        dr_enable=0,
+        # per-parameter randomisation schema (dr_utils.py:71-132): (distribution, operation, lo|mu, hi|sigma, schedule, schedule_steps)
+        # for mass, ixx, iyy, izz, arm, thrust scale, yaw_km -- default: scaling x uniform [0.8, 1.2), yaw_km not randomised
+        dr=tuple((DR_UNIFORM, DR_SCALING, 0.8, 1.2, 0, 0) for _ in range(6)) + ((DR_NONE, DR_SCALING, 0.8, 1.2, 0, 0),),
+        wrench_warmup_steps=0,
         pomdp_mode=POMDP_NONE, pomdp_prob=0.0, noise_sigma=0.0,
         plate_enable=0, plate_z=0.377, plate_radius=0.35, land_cutoff=0.0,
     )
@@ -187,8 +194,9 @@ class QuadStepOracle:
 
     def __init__(self, cfg, dtype=torch.float32, exact_trig=False):
         # float fields are rounded to float32 once, exactly as they sit in the C `ozl_cfg` struct
-        self.cfg = {k: (tuple(float(np.float32(x)) for x in v) if isinstance(v, (tuple, list))
-                        else float(np.float32(v)) if isinstance(v, float) else v) for k, v in dict(cfg).items()}
+        r32 = lambda x: float(np.float32(x)) if isinstance(x, float) else x
+        self.cfg = {k: (tuple(tuple(r32(y) for y in x) if isinstance(x, (tuple, list)) else r32(x) for x in v)
+                        if isinstance(v, (tuple, list)) else r32(v)) for k, v in dict(cfg).items()}
         cfg = self.cfg
         self.dtype = dtype
         self.exact_trig = exact_trig      # float64 cross-check of the polynomial sin/cos
@@ -202,11 +210,12 @@ class QuadStepOracle:
         self.target = z(n, 3)
         self.target[:, 2] = 1.0           # ouzelum.py:73
         self.ep_ret = z(n)
-        # per-env parameters: mass, ixx, iyy, izz, arm, thrust scale | fault rotor, onset, effectiveness
-        self.params = z(n, 6)
+        # per-env parameters: mass, ixx, iyy, izz, arm, thrust scale, yaw_km | fault rotor, onset, effectiveness
+        self.params = z(n, 7)
         for j, k in enumerate(("mass", "ixx", "iyy", "izz", "arm")):
             self.params[:, j] = float(np.float32(cfg[k])) if dtype == torch.float32 else cfg[k]
         self.params[:, 5] = 1.0
+        self.params[:, 6] = cfg["yaw_km"]
         self.fault_rotor = torch.zeros(n, dtype=torch.int64)
         self.fault_onset = torch.full((n,), 0x1FFFFFFF, dtype=torch.int64)   # never, until a reset draws one
         self.fault_eff = torch.ones(n, dtype=dtype)
@@ -232,12 +241,45 @@ class QuadStepOracle:
     def _u(self, r):
         return torch.from_numpy(px.u01(r)).to(self.dtype)
 
+    def _dr_apply(self, spec, nominal, r0, r1, step):
+        """One randomised parameter -- isaacgymenvs/utils/dr_utils.py:71-132 (generate_random_samples) with the schedule driven
+        by the step counter; same float32 operations as dr_apply() in ouzelum_b200/csrc/quad_env.cuh."""
+        c = self._c
+        dist, op, lo, hi, sched, steps = spec
+        n = self.n
+        if dist == DR_NONE:
+            return c(nominal).expand(n).clone()
+        a, b = c(lo), c(hi)
+        if sched != DR_SCHED_NONE:
+            inv = torch.tensor(1.0, dtype=self.dtype) / c(float(steps))
+            ss = inv * c(float(min(step, steps))) if sched == DR_SCHED_LINEAR else c(0.0 if step < steps else 1.0)
+            one_m = 1.0 - ss
+            if op == DR_ADDITIVE:
+                a, b = a * ss, b * ss
+            elif dist == DR_GAUSSIAN:
+                a, b = a * ss + one_m, b * ss
+            else:
+                a, b = a * ss + one_m, b * ss + one_m
+        if dist == DR_UNIFORM:
+            smp = a + (b - a) * self._u(r0)
+        elif dist == DR_LOGUNIFORM:
+            la, lb = math.log(float(a)), math.log(float(b))
+            smp = torch.from_numpy(np.exp(la + (lb - la) * px.u01(r0).astype(np.float64))).to(self.dtype)
+        else:
+            u1 = ((r0 >> np.uint32(8)).astype(np.float64) + 1.0) * 5.9604644775390625e-08
+            u2 = px.u01(r1).astype(np.float64)
+            z = np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586 * u2)
+            smp = torch.from_numpy(float(a) + float(b) * z).to(self.dtype)
+        return c(nominal) + smp if op == DR_ADDITIVE else c(nominal) * smp
+
     # ------------------------------------------------------------------ step
-    def step(self, actions, target_in=None, act_mode=0):
+    def step(self, actions, target_in=None, act_mode=0, warmup=None, det_target=None):
         """act_mode 0: rotor thrust-rate actions (ouzelum.py:237-244); 1: body wrench (fz,tx,ty,tz) on the base link
         (lee_landed.py:316-330).  target_in [N,3]: externally driven target (landing.py:373-374)."""
         cfg, c, dt_ = self.cfg, self._c, self.dtype
         seed, t = cfg.get("seed", 0), self.step_count
+        if warmup is None:      # estimator warm-up of the wrench-actuated classical task (ekf_lee_landed.py:339)
+            warmup = act_mode == 1 and t < int(cfg.get("wrench_warmup_steps", 0))
         a = actions.to(dt_)
         if act_mode == 0:
             a = torch.clamp(a, -cfg["clip_actions"], cfg["clip_actions"])                 # vec_task.py:327
@@ -274,25 +316,28 @@ class QuadStepOracle:
             self.fault_onset = torch.where(rst, onset, self.fault_onset)
             self.fault_eff = torch.where(rst, eff, self.fault_eff)
         if cfg["dr_enable"]:
-            r = px.draw(seed, self.env_ids, t, px.P_DR0) + px.draw(seed, self.env_ids, t, px.P_DR1)[:2]
-            nominal = [cfg["mass"], cfg["ixx"], cfg["iyy"], cfg["izz"], cfg["arm"], 1.0]
-            newp = torch.stack([c(nominal[j]) * (c(cfg["dr_lo"]) + c(cfg["dr_range"]) * self._u(r[j]))
-                                for j in range(6)], -1)
+            r = px.draw(seed, self.env_ids, t, px.P_DR0) + px.draw(seed, self.env_ids, t, px.P_DR1)[:3]
+            r2 = px.draw(seed, self.env_ids, t, px.P_DR2) + px.draw(seed, self.env_ids, t, px.P_DR3)[:3]
+            nominal = [cfg["mass"], cfg["ixx"], cfg["iyy"], cfg["izz"], cfg["arm"], 1.0, cfg["yaw_km"]]
+            newp = torch.stack([self._dr_apply(cfg["dr"][j], nominal[j], r[j], r2[j], t) for j in range(7)], -1)
             self.params = torch.where(rst[:, None], newp, self.params)
 
         # landing detector (landed.py:288-295): pre-step position, target as left by the previous step
         cut = torch.zeros_like(rst)
         if cfg.get("land_cutoff", 0.0) > 0:
-            d0 = self.target - self.root[:, 0:3]
+            # det_target: the point the detector measures to (LeeLanded: the controller target, lee_landed.py:305,318-322)
+            d0 = (self.target if det_target is None else det_target.to(dt_)) - self.root[:, 0:3]
             cut = ieee_sqrt((d0[:, 0] * d0[:, 0] + d0[:, 1] * d0[:, 1]) + d0[:, 2] * d0[:, 2]) < c(cfg["land_cutoff"])
+            if warmup:      # ekf_lee_landed.py:508-529: no flag during the estimator warm-up, hover force applied to every env
+                cut = torch.zeros_like(rst)
             self.landed = self.landed | cut
         if target_in is not None:
             self.target = target_in.to(dt_).clone()
         if act_mode == 1:
             zero = torch.zeros_like(a[:, 0])
-            off = rst | cut
-            fz = torch.where(off, zero, a[:, 0])
-            tau_b = [torch.where(off, zero, a[:, 1 + j]) for j in range(3)]
+            off = cut if warmup else (rst | cut)              # forces[reset_env_ids] = 0 -- the torque tensor is NOT cleared for
+            fz = torch.where(off, zero, a[:, 0])              # just-reset envs (lee_landed.py:324-325, ekf_lee_landed.py:519-520)
+            tau_b = [torch.where(cut, zero, a[:, 1 + j]) for j in range(3)]
             self.thrust = torch.where(rst[:, None], torch.zeros_like(self.thrust), self.thrust)
             fault_active = torch.zeros_like(rst)
             self._simulate(None, wrench=(fz, tau_b))
@@ -405,7 +450,7 @@ class QuadStepOracle:
             fz = ((f0 + f1) + f2) + f3
             tau_b = [arm * (((f1 - f0) + f2) - f3),
                      arm * (((f1 - f0) - f2) + f3),
-                     c(cfg["yaw_km"]) * (((f2 - f0) - f1) + f3)]
+                     P[:, 6] * (((f2 - f0) - f1) + f3)]
         R = quat_to_R(q)
         b3 = [R[0][2], R[1][2], R[2][2]]
         fw = _matvec(R, body_force) if body_force is not None else [b3[j] * fz for j in range(3)]
@@ -476,6 +521,36 @@ class QuadStepOracle:
         self.root = out
 
     # ------------------------------------------------------------------ state access (parity tests)
+    def post_reset_root(self):
+        """Root state as `reset_idx` leaves it for the envs flagged in reset_buf (spawn draws of the CURRENT step), without
+        stepping: what the estimator / controller code of the classical tasks sees (reset_idx runs first in
+        pre_physics_step, ekf_lee_landed.py:312-314)."""
+        cfg, c = self.cfg, self._c
+        rst = self.reset_buf != 0
+        r0, r1, r2, _ = px.draw(cfg.get("seed", 0), self.env_ids, self.step_count, px.P_SPAWN)
+        u = [self._u(r) for r in (r0, r1, r2)]
+        spawn = torch.zeros(self.n, 13, dtype=self.dtype)
+        for j in range(3):
+            spawn[:, j] = c(cfg["spawn_base"][j]) + (c(cfg["spawn_range"][j]) * u[j] + c(cfg["spawn_lo"][j]))
+        spawn[:, 6] = 1.0
+        return torch.where(rst[:, None], spawn, self.root)
+
+    def load(self, root, thrust, target, ep_ret, params8, fault2, reset_buf, progress_buf, step_count):
+        """Adopt the device-side state of an env handle (ozl_get_state / ozl_get_params layouts) so that ONE step can be compared
+        from identical state.  params8 = mass, ixx, iyy, izz, arm, thrust scale, fault effectiveness, yaw_km; fault2 = rotor,
+        onset | landed << 31."""
+        t = lambda x, dt=None: torch.as_tensor(np.asarray(x)).to(dt or self.dtype).clone()
+        self.root, self.thrust, self.target, self.ep_ret = t(root), t(thrust), t(target), t(ep_ret)
+        p = t(params8)
+        self.params = torch.cat([p[:, 0:6], p[:, 7:8]], 1)
+        self.fault_eff = p[:, 6].clone()
+        f = torch.as_tensor(np.asarray(fault2)).to(torch.int64)
+        self.fault_rotor = f[:, 0].clone()
+        self.fault_onset = f[:, 1] & 0x1FFFFFFF
+        self.landed = f[:, 1] < 0
+        self.reset_buf, self.progress_buf = t(reset_buf, torch.int64), t(progress_buf, torch.int64)
+        self.step_count = int(step_count)
+
     def get_state(self):
         return dict(root=self.root.clone(), thrust=self.thrust.clone(), target=self.target.clone(),
                     ep_ret=self.ep_ret.clone(), params=self.params.clone(),

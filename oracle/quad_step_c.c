@@ -12,7 +12,7 @@
 #include <string.h>
 #include "ouzelum_b200.h"
 
-enum { P_TARGET = 0, P_SPAWN = 1, P_FAULT = 2, P_DR0 = 3, P_DR1 = 4, P_OBSNOISE = 8, P_FLICKER = 12 };
+enum { P_TARGET = 0, P_SPAWN = 1, P_FAULT = 2, P_DR0 = 3, P_DR1 = 4, P_OBSNOISE = 8, P_FLICKER = 12, P_DR2 = 24, P_DR3 = 25 };
 #define GLOBAL_ENV 0xFFFFFFFFu
 #define FAULT_NEVER 0x1FFFFFFF
 
@@ -29,6 +29,29 @@ static void draw(uint64_t seed, uint32_t env, uint64_t step, uint32_t purpose, u
     philox(env, (uint32_t)step, (uint32_t)(step >> 32), purpose, (uint32_t)seed, (uint32_t)(seed >> 32), out);
 }
 static float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
+
+/* one domain-randomised parameter (isaacgymenvs/utils/dr_utils.py:71-132); same operations as dr_apply() in quad_env.cuh */
+static float dr_apply(const ozl_dr_param* d, float nominal, uint32_t r0, uint32_t r1, uint64_t step) {
+    if (d->distribution == OZL_DR_NONE) return nominal;
+    float a = d->range[0], b = d->range[1];
+    if (d->schedule != OZL_DR_SCHED_NONE) {
+        const uint64_t lim = (uint64_t)d->schedule_steps;
+        const float inv_steps = 1.0f / (float)d->schedule_steps;
+        const float ss = d->schedule == OZL_DR_SCHED_LINEAR ? inv_steps * (float)(step < lim ? step : lim) : (step < lim ? 0.0f : 1.0f);
+        const float one_m = 1.0f - ss;
+        if (d->operation == OZL_DR_ADDITIVE) { a = a * ss; b = b * ss; }
+        else if (d->distribution == OZL_DR_GAUSSIAN) { a = a * ss + one_m; b = b * ss; }
+        else { a = a * ss + one_m; b = b * ss + one_m; }
+    }
+    float smp;
+    if (d->distribution == OZL_DR_UNIFORM) smp = a + (b - a) * u01(r0);
+    else if (d->distribution == OZL_DR_LOGUNIFORM) { const double la = log((double)a), lb = log((double)b); smp = (float)exp(la + (lb - la) * (double)u01(r0)); }
+    else {
+        const double u1 = ((double)(r0 >> 8) + 1.0) * 5.9604644775390625e-08, u2 = (double)u01(r1);
+        smp = (float)((double)a + (double)b * (sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2)));
+    }
+    return d->operation == OZL_DR_ADDITIVE ? nominal + smp : nominal * smp;
+}
 
 typedef struct {
     float h, hh, hh2, max_angvel2, inv3, half, inv_pi, flicker_p, noise_lo, noise_range;
@@ -56,8 +79,8 @@ static void cross3(const float a[3], const float b[3], float o[3]) {
     o[0] = fmaf(a[1], b[2], -(a[2] * b[1])); o[1] = fmaf(a[2], b[0], -(a[0] * b[2])); o[2] = fmaf(a[0], b[1], -(a[1] * b[0]));
 }
 
-/* state arrays (AoS, caller-owned): root [n,13], thrust [n,4], target [n,3], ep_ret [n], params [n,7] =
- * mass,ixx,iyy,izz,arm,thrust_scale,fault_eff, fault [n,2] = rotor, onset */
+/* state arrays (AoS, caller-owned): root [n,13], thrust [n,4], target [n,3], ep_ret [n], params [n,8] =
+ * mass,ixx,iyy,izz,arm,thrust_scale,fault_eff,yaw_km, fault [n,2] = rotor, onset */
 void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, float* thrust, float* target, float* ep_ret,
                      float* params, int32_t* fault, const float* actions, float* obs, float* rew, int64_t* reset,
                      int64_t* progress, uint8_t* timeout) {
@@ -80,7 +103,7 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         const uint32_t genv = (uint32_t)c->env_id_base + (uint32_t)i;
-        float* rs = root + i * 13; float* T = thrust + i * 4; float* tg = target + i * 3; float* pr = params + i * 7;
+        float* rs = root + i * 13; float* T = thrust + i * 4; float* tg = target + i * 3; float* pr = params + i * 8;
         float p[3] = {rs[0], rs[1], rs[2]}, q[4] = {rs[3], rs[4], rs[5], rs[6]}, v[3] = {rs[7], rs[8], rs[9]}, w[3] = {rs[10], rs[11], rs[12]};
         int64_t prog = progress[i];
         const int rst = reset[i] != 0;
@@ -104,14 +127,18 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
                 pr[6] = c->fault_eff_lo + c->fault_eff_range * u01(r4[2]);
             }
             if (c->dr_enable) {
-                uint32_t a[4], b[4];
+                uint32_t a[4], b[4], a2[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};
+                int any_gauss = 0;
+                for (int j = 0; j < OZL_DR_NUM; ++j) any_gauss |= c->dr[j].distribution == OZL_DR_GAUSSIAN;
                 draw(c->seed, genv, step, P_DR0, a); draw(c->seed, genv, step, P_DR1, b);
-                pr[0] = c->mass * (c->dr_lo + c->dr_range * u01(a[0]));
-                pr[1] = c->ixx * (c->dr_lo + c->dr_range * u01(a[1]));
-                pr[2] = c->iyy * (c->dr_lo + c->dr_range * u01(a[2]));
-                pr[3] = c->izz * (c->dr_lo + c->dr_range * u01(a[3]));
-                pr[4] = c->arm * (c->dr_lo + c->dr_range * u01(b[0]));
-                pr[5] = 1.0f * (c->dr_lo + c->dr_range * u01(b[1]));
+                if (any_gauss) { draw(c->seed, genv, step, P_DR2, a2); draw(c->seed, genv, step, P_DR3, b2); }
+                pr[0] = dr_apply(&c->dr[OZL_DR_MASS], c->mass, a[0], a2[0], step);
+                pr[1] = dr_apply(&c->dr[OZL_DR_IXX], c->ixx, a[1], a2[1], step);
+                pr[2] = dr_apply(&c->dr[OZL_DR_IYY], c->iyy, a[2], a2[2], step);
+                pr[3] = dr_apply(&c->dr[OZL_DR_IZZ], c->izz, a[3], a2[3], step);
+                pr[4] = dr_apply(&c->dr[OZL_DR_ARM], c->arm, b[0], b2[0], step);
+                pr[5] = dr_apply(&c->dr[OZL_DR_THRUST_SCALE], 1.0f, b[1], b2[1], step);
+                pr[7] = dr_apply(&c->dr[OZL_DR_YAW_KM], c->yaw_km, b[2], b2[2], step);
             }
         }
         /* thrust command (ouzelum.py:237-248) */
@@ -132,7 +159,7 @@ void ozl_oracle_step(const ozl_cfg* c, uint64_t step, int64_t n, float* root, fl
         const float hi[3] = {d.h * (1.0f / pr[1]), d.h * (1.0f / pr[2]), d.h * (1.0f / pr[3])};
         const float fz = ((F[0] + F[1]) + F[2]) + F[3];
         const float tau_b[3] = {pr[4] * (((F[1] - F[0]) + F[2]) - F[3]), pr[4] * (((F[1] - F[0]) - F[2]) + F[3]),
-                                c->yaw_km * (((F[2] - F[0]) - F[1]) + F[3])};
+                                pr[7] * (((F[2] - F[0]) - F[1]) + F[3])};
         float R[3][3], fw[3], tau_w[3], aw[3], rc[3], x[3], t3[3], wb[3], tb[3];
         quat_to_R(q, R);
         for (int j = 0; j < 3; ++j) fw[j] = R[j][2] * fz;

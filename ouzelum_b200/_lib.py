@@ -9,7 +9,22 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OUZELUM_B200_LIB") or os.path.join(_HERE, "libouzelum_b200.so")   # override: kernel experiments only
 
-OZL_ABI_VERSION = 2
+OZL_ABI_VERSION = 3
+
+
+DR_NONE, DR_UNIFORM, DR_LOGUNIFORM, DR_GAUSSIAN = 0, 1, 2, 3
+DR_SCALING, DR_ADDITIVE = 0, 1
+DR_SCHED_NONE, DR_SCHED_LINEAR, DR_SCHED_CONSTANT = 0, 1, 2
+DR_PARAMS = ("mass", "ixx", "iyy", "izz", "arm", "thrust_scale", "yaw_km")     # index = OZL_DR_*
+
+
+class OzlDrParam(C.Structure):
+    """Mirror of `struct ozl_dr_param` (include/ouzelum_b200.h)."""
+    _fields_ = [("distribution", C.c_int32), ("operation", C.c_int32), ("range", C.c_float * 2),
+                ("schedule", C.c_int32), ("schedule_steps", C.c_int32)]
+
+    def to_tuple(self):
+        return (self.distribution, self.operation, float(self.range[0]), float(self.range[1]), self.schedule, self.schedule_steps)
 
 
 class OzlCfg(C.Structure):
@@ -28,9 +43,10 @@ class OzlCfg(C.Structure):
         ("arm", C.c_float), ("com_z", C.c_float), ("max_angvel", C.c_float),
         ("lin_drag", C.c_float), ("yaw_km", C.c_float),
         ("fault_mode", C.c_int32), ("fault_eff_lo", C.c_float), ("fault_eff_range", C.c_float),
-        ("dr_enable", C.c_int32), ("dr_lo", C.c_float), ("dr_range", C.c_float),
+        ("dr_enable", C.c_int32), ("dr", OzlDrParam * 7),
         ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float), ("noise_sigma", C.c_float),
         ("collect_metrics", C.c_int32), ("plate_enable", C.c_int32), ("plate_z", C.c_float), ("plate_radius", C.c_float), ("land_cutoff", C.c_float),
+        ("wrench_warmup_steps", C.c_int32), ("reserved1", C.c_int32),
     ]
 
     def to_dict(self):
@@ -39,14 +55,25 @@ class OzlCfg(C.Structure):
             if name.startswith("reserved") or name == "abi_version":
                 continue
             v = getattr(self, name)
-            out[name] = tuple(v) if hasattr(v, "__len__") else v
+            if name == "dr":
+                out[name] = tuple(d.to_tuple() for d in v)
+            else:
+                out[name] = tuple(v) if hasattr(v, "__len__") else v
         return out
 
     def update(self, **kw):
         for k, v in kw.items():
             if k not in dict(self._fields_):
                 raise KeyError(f"ozl_cfg has no field {k!r}")
-            if isinstance(v, (tuple, list)):
+            if k == "dr":                      # {index or name: (distribution, operation, lo, hi[, schedule, schedule_steps])}
+                for key, spec in (v.items() if isinstance(v, dict) else enumerate(v)):
+                    j = DR_PARAMS.index(key) if isinstance(key, str) else int(key)
+                    spec = tuple(spec)
+                    spec = spec + (0, 0)[:6 - len(spec)]
+                    d = self.dr[j]
+                    d.distribution, d.operation, d.schedule, d.schedule_steps = int(spec[0]), int(spec[1]), int(spec[4]), int(spec[5])
+                    d.range[0], d.range[1] = float(spec[2]), float(spec[3])
+            elif isinstance(v, (tuple, list)):
                 getattr(self, k)[:] = [float(x) for x in v]
             else:
                 setattr(self, k, v)
@@ -56,7 +83,7 @@ class OzlCfg(C.Structure):
 class OzlHostIo(C.Structure):
     """Mirror of `struct ozl_host_io` (include/ouzelum_b200.h)."""
     _fields_ = [("actions_host", C.c_void_p), ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("done_host", C.c_void_p),
-                ("reset", C.c_void_p), ("progress", C.c_void_p), ("timeout", C.c_void_p), ("ep_ret", C.c_void_p)]
+                ("reset_host", C.c_void_p), ("reset", C.c_void_p), ("progress", C.c_void_p), ("timeout", C.c_void_p), ("ep_ret", C.c_void_p)]
 
 
 class OzlPvArgs(C.Structure):
@@ -91,9 +118,14 @@ class OzlEkfLeeArgs(C.Structure):
         ("dt", C.c_float), ("mg", C.c_float), ("hover_force", C.c_float), ("convergence_steps", C.c_int64),
         ("pomdp_mode", C.c_int32), ("pomdp_prob", C.c_float),
         ("pos_period", C.c_uint32), ("pos_phase", C.c_uint32), ("vel_period", C.c_uint32), ("vel_phase", C.c_uint32),
-        ("per_env_triggers", C.c_int32), ("acc_var", C.c_float * 3), ("pos_var", C.c_float * 3),
+        ("per_env_triggers", C.c_int32), ("num_envs_total", C.c_int64), ("acc_var", C.c_float * 3), ("pos_var", C.c_float * 3),
         ("ekf_Dt", C.c_double), ("ekf_g_noise", C.c_double),
     ]
+
+
+class OzlLeeLandedArgs(C.Structure):
+    """Mirror of `struct ozl_lee_landed_args` (include/ouzelum_b200.h)."""
+    _fields_ = [("gains16", C.POINTER(C.c_float)), ("cmd", C.c_float * 4), ("mg", C.c_float), ("wrench4", C.c_void_p)]
 
 
 class OzlQuadcopterArgs(C.Structure):
@@ -147,6 +179,8 @@ _SIGS = {
     "ozl_ekf_lee_step": (C.c_int, [_P, C.POINTER(OzlEkfLeeArgs), _P]),
     "ozl_ekf_lee_landed_step": (C.c_int, [_P] * 10),
     "ozl_step_counter_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "ozl_landing_step": (C.c_int, [_P] * 10),
+    "ozl_lee_landed_step": (C.c_int, [_P] * 10),
     "ozl_pomdp_observation": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_int32, _P, _P, _P]),
     "ozl_husky_init": (C.c_int, [C.POINTER(OzlHuskyArgs), _P]),

@@ -3,8 +3,8 @@
 
 Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   Blackwell-only SASS (no PTX fallback for other archs)
-  -fmad=false                                every float op individually rounded => bit-exact against the
-                                             op-ordered CPU oracle (the path is HBM-bound; FMA fusion buys nothing)
+  -fmad=false                                no implicit contraction: every float op is individually rounded and fused
+                                             multiply-adds are explicit (fmaf) => bit-exact against the op-ordered CPU oracles
   -lineinfo                                  ncu source-page attribution
 """
 import os
@@ -16,11 +16,12 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libouzelum_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-# Per-TU floating-point contract.  The env-step kernels are held BIT-EXACT to the op-ordered CPU oracle, so they are compiled
-# without FMA contraction; the estimator / controller kernels are held to tolerances (they call sin/cos/atan2 and run
-# ill-conditioned float32 Kalman updates anyway), so they keep the default contraction (fewer instructions, more accurate).
-FMAD_OFF = {"quad_step.cu", "quadcopter.cu"}
-FMAD = os.environ.get("OZL_COMPANION_FMAD", "true")
+# Floating-point contract: EVERY translation unit is compiled without FMA contraction (-fmad=false); fused multiply-adds are
+# written explicitly (fmaf / fma) where they pay.  The env-step arithmetic is therefore bit-exact against the op-ordered CPU
+# oracles wherever it is instantiated (quad_step.cu, quadcopter.cu AND the one-launch EKFLeeLanded step), and the estimator /
+# controller device functions give identical bits in the fused kernel and in the stand-alone companion kernels.
+FMAD_OFF = None          # all
+FMAD = os.environ.get("OZL_COMPANION_FMAD", "false")
 
 
 def sources():
@@ -44,7 +45,7 @@ def build(force=False, verbose=False):
     for src in sources():
         name = os.path.basename(src)
         obj = os.path.join(objdir, name[:-3] + ".o")
-        fmad = "false" if name in FMAD_OFF else FMAD
+        fmad = "false" if (FMAD_OFF is None or name in FMAD_OFF) else FMAD
         cmd = [NVCC] + FLAGS + ["-fmad=" + fmad] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)

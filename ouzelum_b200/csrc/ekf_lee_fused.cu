@@ -6,6 +6,7 @@
 //   * the step index, warm-up flag and the shared sensor-trigger counters come from the env's DEVICE step counter, so the
 //     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
 //   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
+#define OZL_PHILOX_NOINLINE 1
 #include "internal.h"
 #include "bulk_copy.cuh"
 #include "quad_io.cuh"
@@ -17,7 +18,7 @@
 namespace ozl {
 
 struct EkfLeeArgs {
-    int64_t n;
+    int64_t n, n_total;                   // envs of this handle / of the whole job (all ranks): trigger index = step * n_total + global env
     double* ekf_q;  double* ekf_P;        // [4][n], [16][n]
     float* pv_x;    float* pv_P;          // [9][n], [81][n]
     float* prev_linvel;                   // [n,3]
@@ -43,15 +44,23 @@ struct EkfLeeArgs {
 #define OZL_EKF_MINB 4
 #endif
 constexpr int kEkfBlock = OZL_EKF_BLOCK;
-static_assert(kEkfBlock == kTile, "the one-launch step retires one step-counter work unit per 128-env block (step_counter.cuh)");
+static_assert(kEkfBlock % kTile == 0, "a block covers whole 128-env tiles: one step-counter work unit per tile (step_counter.cuh)");
+static_assert(kEkfBlock >= 96, "the 81 plane copies of the covariance tile are issued by 81 different threads");
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA):
-//   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by thread 0 with 81 TMA
-//     bulk copies (512 B each, one per plane) completing on an mbarrier, issued before anything else: the 41 KB of loads
-//     fly while every thread runs the sensor front-end and the float64 attitude EKF out of registers
+//   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by 81 TMA bulk copies
+//     (one plane each, issued by 81 different threads, completing on one mbarrier) before anything else: the 41 KB of loads fly
+//     while every thread runs the vehicle, the sensor front-end and the float64 attitude EKF out of registers
+//   * everything the later stages read from HBM (EKF / PV state planes, waypoint, the env's static planes, progress) is
+//     prefetched into L2 at the top, and each stage's loads are issued before the previous stage's arithmetic, so no stage
+//     starts with a DRAM round trip on its critical path (round 1: 21 % of the stall samples were `long_scoreboard`)
 //   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared)
 //   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
 //   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
+//   * the counter RNG is called out of line in this TU (OZL_PHILOX_NOINLINE): ~22 draw sites would otherwise add ~25 KB of
+//     straight-line code to a kernel that already exceeds the instruction caches (round 1: 23 % of stalls were `no_instruction`)
 // WITH_STEP = true is the WHOLE EKFLeeLanded control step in one launch (ozl_ekf_lee_landed_step): the ground vehicle that
 // carries the target runs first (targets.cuh), and after the controller the same thread applies its wrench to its env --
 // env_step(ACT_WRENCH) with the vehicle's target, sensor-fault epilogue on the observation, stores, episode statistics and
@@ -76,14 +85,35 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     griddep_wait();                    // PDL (bulk_copy.cuh): everything below reads what the previous launch wrote
     griddep_launch_dependents();
     if (tid == 0) s_step = read_step(pl.ctrl);
-    __syncthreads();
-    if (use_tma) {
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)n_here * 4u;
-            mbar_expect_tx(&s_bar, 81u * bytes);
-#pragma unroll 1
-            for (int k = 0; k < 81; ++k) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
+    // ---- stage-0 loads (registers) and L2 prefetches of everything the later stages will read
+    bool rst = false;
+    float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+    float wz0 = 0.f, pvl[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+        rst = a.reset[i] != 0;
+        d0 = *plane4_ptr(pl, 0, i); d1 = *plane4_ptr(pl, 1, i); d2 = *plane4_ptr(pl, 2, i);
+        wz0 = plane4_ptr(pl, 3, i)->x;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pvl[j] = a.prev_linvel[i * 3 + j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prefetch_l2(a.ekf_q + (int64_t)k * a.n + i);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) prefetch_l2(a.ekf_P + (int64_t)k * a.n + i);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) prefetch_l2(a.pv_x + (int64_t)k * a.n + i);
+        prefetch_l2(a.waypoint + i * 3);
+        if (WITH_STEP) {
+            prefetch_l2(plane2_ptr(pl, i));
+#pragma unroll
+            for (int k = 4; k < 7; ++k) prefetch_l2(plane4_ptr(pl, k, i));
+            prefetch_l2(io.progress + i);
         }
+    }
+    __syncthreads();                   // the mbarrier is initialised, the step index is published
+    if (use_tma) {
+        const uint32_t bytes = (uint32_t)n_here * 4u;
+        if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
+        if (tid < 81) bulk_load_g2s(s_P + tid * kEkfBlock, a.pv_P + (int64_t)tid * a.n + base, bytes, &s_bar);
     } else if (valid) {
 #pragma unroll 9
         for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
@@ -94,9 +124,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     // live across the block barrier that precedes the drain of the covariance tile: controller inputs
     float q[4], w[3], est_p[3], est_v[3], cmd[4];
     float tgt[3] = {0.f, 0.f, 0.f};
-    bool rst = false;
     if (valid) {
-        rst = a.reset[i] != 0;
         if (WITH_STEP) husky_step_env(h, i, step, tgt);     // landing target for this step (landing.py:373-374)
         // ---- true root state (post reset_idx)
         float p[3], v[3];
@@ -108,18 +136,21 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             q[0] = q[1] = q[2] = 0.f; q[3] = 1.f;
             for (int j = 0; j < 3; ++j) { v[j] = 0.f; w[j] = 0.f; }
         } else {
-            const float4 d0 = *plane4_ptr(pl, 0, i), d1 = *plane4_ptr(pl, 1, i), d2 = *plane4_ptr(pl, 2, i);
-            const float wz = plane4_ptr(pl, 3, i)->x;
             p[0] = d0.x; p[1] = d0.y; p[2] = d0.z; q[0] = d0.w; q[1] = d1.x; q[2] = d1.y; q[3] = d1.z;
-            v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz;
+            v[0] = d1.w; v[1] = d2.x; v[2] = d2.y; w[0] = d2.z; w[1] = d2.w; w[2] = wz0;
         }
+        // ---- attitude-EKF state: loads issued here (L2 hits), consumed after the sensor front-end
+        EKF4 s;
+        if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
+        else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
+        for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
         // ---- sensor front-end (:345-346,366-375,397-406)
         FaultCfg f = a.f;
         f.step = step;
         if (warm) f.mode = 0;
         float acc[3], gyr[3], ang[4], pos[3], vel[3];
         for (int j = 0; j < 3; ++j) {
-            acc[j] = (v[j] - a.prev_linvel[i * 3 + j]) / a.dt;
+            acc[j] = (v[j] - pvl[j]) / a.dt;
             gyr[j] = w[j]; pos[j] = p[j]; vel[j] = v[j];
             a.prev_linvel[i * 3 + j] = v[j];                                              // :454
         }
@@ -130,13 +161,13 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         sensor_fault(f, genv, 4, false, acc, 3);
         sensor_fault(f, genv, 5, false, pos, 3);
         sensor_fault(f, genv, 6, false, vel, 3);
+        // ---- PV state: loads issued before the EKF arithmetic, consumed after it
+        PVShared<kEkfBlock> pvs;
+        pvs.P = s_P + tid;
+        for (int k = 0; k < 9; ++k) pvs.x[k] = a.pv_x[(int64_t)k * a.n + i];
         // ---- attitude EKF (:348-352,378-391), float64 in registers
         float q32[4];
         {
-            EKF4 s;
-            if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
-            else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
-            for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
             const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
             const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
             ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
@@ -145,19 +176,18 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         }
         // ---- PV filter (:353-358,397-444) on the shared-memory covariance tile
         {
-            PVShared<kEkfBlock> s;
-            s.P = s_P + tid;
-            for (int k = 0; k < 9; ++k) s.x[k] = a.pv_x[(int64_t)k * a.n + i];
-            if (rst) { for (int k = 0; k < 3; ++k) { s.x[k] = p[k]; s.x[3 + k] = v[k]; s.x[6 + k] = 0.f; } }
+            if (rst) { for (int k = 0; k < 3; ++k) { pvs.x[k] = p[k]; pvs.x[3 + k] = v[k]; pvs.x[6 + k] = 0.f; } }
             const float qt[4] = {q[3], q[0], q[1], q[2]};
             if (use_tma) mbar_wait(&s_bar, 0);                    // the covariance tile has landed
-            pv_predict(s, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
-            const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n + (uint64_t)i;   // shared counters (:425-440)
-            if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(s, pos, a.pos_var);
+            pv_predict(pvs, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
+            // shared sensor-trigger counters (:425-440): the reference advances them once per env-iteration, i.e. the k-th
+            // iteration overall is step * N_total + GLOBAL env id (invariant to how the envs are sharded over GPUs)
+            const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n_total + (uint64_t)genv;
+            if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(pvs, pos, a.pos_var);
             const float zero3[3] = {0.f, 0.f, 0.f};
-            if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(s, vel, zero3);  // gps_var=None => R = 0
-            for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = s.x[kk];
-            for (int kk = 0; kk < 3; ++kk) { est_p[kk] = s.x[kk]; est_v[kk] = s.x[3 + kk]; }
+            if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(pvs, vel, zero3);  // gps_var=None => R = 0
+            for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = pvs.x[kk];
+            for (int kk = 0; kk < 3; ++kk) { est_p[kk] = pvs.x[kk]; est_v[kk] = pvs.x[3 + kk]; }
         }
         if (!use_tma) {
 #pragma unroll 9
@@ -180,15 +210,17 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         cmd[0] = wp[0] * a.g.scale[0]; cmd[1] = wp[1] * a.g.scale[1]; cmd[2] = wp[2] * a.g.scale[2]; cmd[3] = 0.0f;
     }
     if (use_tma) {
-        // drain: every thread's filter writes are made visible to the async proxy, then thread 0 issues the bulk stores
+        // drain: every thread's filter writes are made visible to the async proxy, then 81 threads issue one plane store each
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)n_here * 4u;
-#pragma unroll 1
-            for (int k = 0; k < 81; ++k) bulk_store_s2g_issue(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, bytes);
-            bulk_commit();
-        }
+        if (tid < 81) bulk_store_s2g(a.pv_P + (int64_t)tid * a.n + base, s_P + tid * kEkfBlock, (uint32_t)n_here * 4u);
+    }
+    // the env's remaining planes for the step below: loads issued before the controller arithmetic (L2 hits by now)
+    Loaded L;
+    int64_t prog = 0;
+    if (WITH_STEP && valid) {
+        load_env(pl, i, L);
+        prog = io.progress[i];
     }
     float4 wr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
@@ -201,7 +233,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         }
         a.wrench[i] = wr;
     }
-    if (use_tma && tid == 0) bulk_wait_read_all();      // the tile must stay alive until the bulk stores have read it
+    if (use_tma && tid < 81) bulk_wait_read_all();      // the tile must stay alive until the bulk stores have read it
     if (!WITH_STEP) return;
 
     // ---- the env step itself (quad_step_kernel's body, wrench actuation, target from the vehicle)
@@ -211,9 +243,6 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     float* s_obs = s_P;                                  // reused: [kEkfBlock][13] observation tile
     __syncthreads();                                     // every thread is done with its covariance column, drain has read the tile
     if (valid) {
-        Loaded L;
-        load_env(pl, i, L);
-        const int64_t prog = io.progress[i];
         Env e;
         unpack(L, e);
         const float act[4] = {wr.x, wr.y, wr.z, wr.w};
@@ -240,7 +269,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             for (int k = tid; k < nflt; k += kEkfBlock) dst[k] = s_obs[k];
         }
     }
-    block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, 1ull + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
+    block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, (unsigned long long)((n_here + kTile - 1) / kTile) + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
     if (tid == 0) bulk_wait_read_all();
 }
 
@@ -257,6 +286,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     if (in->pomdp_mode < 0 || in->pomdp_mode > 3) return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");
     EkfLeeArgs a;
     a.n = env->cfg.num_envs;
+    a.n_total = in->num_envs_total > 0 ? in->num_envs_total : env->cfg.num_envs;
     a.ekf_q = in->ekf_q4xN; a.ekf_P = in->ekf_P16xN; a.pv_x = in->pv_x9xN; a.pv_P = in->pv_P81xN;
     a.prev_linvel = in->prev_linvel3; a.waypoint = in->waypoint3; a.target = in->target3; a.reset = in->reset;
     a.wrench = (float4*)in->wrench4; a.est13 = in->est13; a.cmd4 = (float4*)in->cmd4;

@@ -19,7 +19,7 @@ constexpr int kMetricStride = 32;      // doubles per slot (16 used)
 // Private state of one handle: float4-packed planes, so one env == one 16-byte lane per plane.
 //   dynamic (read+written every step):  d0 {px,py,pz,qx} d1 {qy,qz,qw,vx} d2 {vy,vz,wx,wy} d3 {wz,T0,T1,T2} d4 {T3,ep_ret}
 //   static  (read every step, written only on reset/resample):
-//           s0 {tx,ty,tz,fault_eff} s1 {1/mass,ixx,iyy,izz} s2 {arm,thrust_scale,fault_word,mass}
+//           s0 {tx,ty,tz,fault_eff} s1 {mass,ixx,iyy,izz} s2 {arm,thrust_scale,fault_word,yaw_km}
 // Layout (OZL_TILED=1, default): tiles of kTile = 128 envs; inside a tile the planes are stored back to back
 //   [d0 2 KiB][d1][d2][d3][d4 1 KiB][s0 2 KiB][s1][s2]  = 15360 bytes per tile
 // so the CTA that owns a tile reads ONE contiguous 15 KiB region and writes ONE contiguous 9 KiB region (long DRAM bursts,

@@ -9,8 +9,10 @@ enum : uint32_t {
     P_TARGET = 0,    // r0,r1 -> target x,y ; r2 -> target z
     P_SPAWN = 1,     // r0,r1,r2 -> spawn offsets
     P_FAULT = 2,     // r0 -> rotor ; r1 -> onset ; r2 -> effectiveness
-    P_DR0 = 3,       // mass, Ixx, Iyy, Izz scalings
-    P_DR1 = 4,       // arm, thrust-scale scalings
+    P_DR0 = 3,       // mass, Ixx, Iyy, Izz
+    P_DR1 = 4,       // arm, thrust-scale, yaw_km
+    P_DR2 = 24,      // second uniforms of gaussian draws (mass, Ixx, Iyy, Izz)
+    P_DR3 = 25,      //                                   (arm, thrust-scale, yaw_km)
     P_QDOF0 = 5,     // Quadcopter task: initial DOF positions 0..3
     P_QDOF1 = 6,     //                  initial DOF positions 4..7
     P_OBSNOISE = 8,  // +0..+3: 13 sensor-noise uniforms
@@ -20,7 +22,15 @@ enum : uint32_t {
 };
 constexpr uint32_t GLOBAL_ENV = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+// OZL_PHILOX_NOINLINE (defined by a TU before including this header): keep ONE copy of the 10 rounds and call it.  The fused
+// EKFLeeLanded kernel has ~22 draw sites (~70 instructions each inlined); out of line its code shrinks by ~20 KB, which matters
+// there because the kernel is far larger than the 32 KB L1.5 instruction cache.  The step kernels keep it inline (measured).
+#ifdef OZL_PHILOX_NOINLINE
+#define OZL_PHILOX_ATTR __noinline__
+#else
+#define OZL_PHILOX_ATTR __forceinline__
+#endif
+static __device__ OZL_PHILOX_ATTR uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {

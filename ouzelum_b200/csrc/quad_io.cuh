@@ -20,8 +20,8 @@ __device__ __forceinline__ void unpack(const Loaded& L, Env& e) {
     e.T[0] = L.d3.y; e.T[1] = L.d3.z; e.T[2] = L.d3.w; e.T[3] = L.d4.x;
     e.ep_ret = L.d4.y;
     e.tgt[0] = L.s0.x; e.tgt[1] = L.s0.y; e.tgt[2] = L.s0.z; e.eff = L.s0.w;
-    e.inv_m = L.s1.x; e.ixx = L.s1.y; e.iyy = L.s1.z; e.izz = L.s1.w;
-    e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z); e.mass = L.s2.w;
+    e.mass = L.s1.x; e.ixx = L.s1.y; e.iyy = L.s1.z; e.izz = L.s1.w;
+    e.arm = L.s2.x; e.ks = L.s2.y; e.fault = __float_as_uint(L.s2.z); e.km = L.s2.w;
 }
 __device__ __forceinline__ void load_env(const Planes& pl, int64_t i, Loaded& L) {
     L.d0 = *plane4_ptr(pl, 0, i); L.d1 = *plane4_ptr(pl, 1, i); L.d2 = *plane4_ptr(pl, 2, i); L.d3 = *plane4_ptr(pl, 3, i);
@@ -37,8 +37,8 @@ __device__ __forceinline__ void store_dynamic(const Planes& pl, int64_t i, const
 }
 __device__ __forceinline__ void store_static(const Planes& pl, int64_t i, const Env& e) {
     *plane4_ptr(pl, 4, i) = make_float4(e.tgt[0], e.tgt[1], e.tgt[2], e.eff);
-    *plane4_ptr(pl, 5, i) = make_float4(e.inv_m, e.ixx, e.iyy, e.izz);
-    *plane4_ptr(pl, 6, i) = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.mass);
+    *plane4_ptr(pl, 5, i) = make_float4(e.mass, e.ixx, e.iyy, e.izz);
+    *plane4_ptr(pl, 6, i) = make_float4(e.arm, e.ks, __uint_as_float(e.fault), e.km);
 }
 
 // Episode statistics (K6) + step-counter retirement at the end of a block.

@@ -8,6 +8,8 @@
 #include "internal.h"
 #include "bulk_copy.cuh"
 #include "quad_io.cuh"
+#include "targets.cuh"
+#include "lee_control.cuh"
 
 namespace ozl {
 
@@ -35,12 +37,27 @@ int check_cuda(cudaError_t e, const char* what) {
 #ifndef OZL_STEP_MINB
 #define OZL_STEP_MINB 7
 #endif
-template <int BLOCK>
+// FRONT selects what runs in front of the env step inside the same thread (one launch per control step for every task):
+//   FRONT_NONE     nothing: Ouzelum, Lando, the tracking / wrench variants fed from caller buffers
+//   FRONT_VEHICLE  the waypoint-following ground vehicle that carries the target (targets.cuh): Landing, Landed
+//   FRONT_LEE      vehicle + Lee position controller on the TRUE state after reset_idx, wrench actuation, landing detector
+//                  on the controller target: LeeLanded (lee_landed.py:263-330)
+enum { FRONT_NONE = 0, FRONT_VEHICLE = 1, FRONT_LEE = 2 };
+struct FrontArgs {
+    HuskyArgs h;
+    LeeGains g;
+    float cmd[4];        // controller target (x, y, z, yaw), lee_landed.py:299-302
+    float mg;            // thrust scale 2 * 9.81, lee_landed.py:296
+    float4* wrench_out;  // optional [N] debug output
+};
+
+template <int BLOCK, int FRONT>
 __global__ void __launch_bounds__(BLOCK, OZL_STEP_MINB)
 quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ actions, float* __restrict__ obs,
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
-                 const int act_mode, uint8_t* __restrict__ done_u8, const int obs_bulk, const int64_t env0) {
+                 const int act_mode, uint8_t* __restrict__ done_u8, int64_t* __restrict__ reset_mirror, const int obs_bulk,
+                 const int64_t env0, const FrontArgs fa) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
     __shared__ uint64_t s_step;
 
@@ -62,7 +79,7 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
     bool rst = false;
     if (valid) {
         load_env(pl, i, L);
-        a4 = __ldg(actions + i);
+        if (FRONT != FRONT_LEE) a4 = __ldg(actions + i);
         prog = progress[i];
         rst = reset[i] != 0;
     }
@@ -72,22 +89,38 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
         Env e;
         unpack(L, e);
         float tnew[3];
-        if (target_in) {     // externally driven target (landing family: target rides on the ground vehicle, landing.py:373-374)
+        const float* tptr = nullptr;
+        if (FRONT != FRONT_NONE) {   // the vehicle moves first; its top plate is this step's target (landing.py:373-374)
+            husky_step_env(fa.h, i, step, tnew);
+            tptr = tnew;
+        } else if (target_in) {      // externally driven target (caller buffer)
             tnew[0] = target_in[i * 3]; tnew[1] = target_in[i * 3 + 1]; tnew[2] = target_in[i * 3 + 2];
+            tptr = tnew;
         }
-        const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+        float act[4] = {a4.x, a4.y, a4.z, a4.w};
         const uint32_t genv = c.env_id_base + (uint32_t)i;
-        env_step(e, act, prog, rst, genv, step, c, o, act_mode, target_in ? tnew : nullptr);
+        if (FRONT == FRONT_LEE) {
+            const int64_t prog1 = env_reset_phase(e, prog, rst, genv, step, c, o);
+            const float cmd[4] = {fa.cmd[0] * fa.g.scale[0], fa.cmd[1] * fa.g.scale[1], fa.cmd[2] * fa.g.scale[2], fa.cmd[3] * fa.g.scale[3]};
+            float th, tq[3];
+            lee_control(LEE_POSITION, e.p, e.q, e.v, e.w, cmd, fa.g, th, tq);                  // lee_landed.py:311
+            act[0] = fa.mg * th; act[1] = tq[0]; act[2] = tq[1]; act[3] = tq[2];                 // :313-314
+            if (fa.wrench_out) fa.wrench_out[i] = make_float4(act[0], act[1], act[2], act[3]);
+            env_act_phase(e, act, prog1, rst, genv, step, c, o, ACT_WRENCH, tptr, fa.cmd);       // detector on the controller target, :305,318-322
+        } else {
+            env_step(e, act, prog, rst, genv, step, c, o, act_mode, tptr);
+        }
         obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
 
         store_dynamic(pl, i, e);
-        if (o.static_dirty || target_in) store_static(pl, i, e);
+        if (o.static_dirty || tptr) store_static(pl, i, e);
         rew[i] = o.rew;
         reset[i] = o.reset ? 1 : 0;
         progress[i] = o.prog;
         if (timeout) timeout[i] = o.timeout ? 1 : 0;
         if (ep_ret_out) ep_ret_out[i] = o.ep_ret_done;
         if (done_u8) done_u8[i] = o.reset ? 1 : 0;
+        if (reset_mirror) reset_mirror[i] = o.reset ? 1 : 0;      // reset_buf with the reference's dtype, for a host consumer
 #pragma unroll
         for (int j = 0; j < 13; ++j) s_obs[threadIdx.x * 13 + j] = o.obs[j];   // stride 13: conflict-free
     }
@@ -405,32 +438,39 @@ __global__ void set_state_kernel(const Planes pl, int64_t n, const float* root13
     store_static(pl, i, e);
 }
 
-__global__ void get_params_kernel(const Planes pl, int64_t n, float* params7, int32_t* fault2) {
+__global__ void get_params_kernel(const Planes pl, int64_t n, float* params8, int32_t* fault2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Loaded L;
     load_env(pl, i, L);
     Env e;
     unpack(L, e);
-    if (params7) {
-        float* p = params7 + i * 7;
-        p[0] = e.mass; p[1] = e.ixx; p[2] = e.iyy; p[3] = e.izz; p[4] = e.arm; p[5] = e.ks; p[6] = e.eff;
+    if (params8) {
+        float* p = params8 + i * 8;
+        p[0] = e.mass; p[1] = e.ixx; p[2] = e.iyy; p[3] = e.izz; p[4] = e.arm; p[5] = e.ks; p[6] = e.eff; p[7] = e.km;
     }
-    if (fault2) { fault2[i * 2] = (int32_t)(e.fault & 3u); fault2[i * 2 + 1] = (int32_t)((e.fault & ~LANDED_BIT) >> 2); }
+    // onset word: bits 0-28 onset, bit 31 = the env's landed flag (so that get -> set round-trips the whole fault word)
+    if (fault2) { fault2[i * 2] = (int32_t)(e.fault & 3u); fault2[i * 2 + 1] = (int32_t)(((e.fault & ~LANDED_BIT) >> 2) | (e.fault & LANDED_BIT)); }
 }
 
-__global__ void set_params_kernel(const Planes pl, int64_t n, const float* params7, const int32_t* fault2) {
+__global__ void set_params_kernel(const Planes pl, int64_t n, const float* params8, const int32_t* fault2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Loaded L;
     load_env(pl, i, L);
     Env e;
     unpack(L, e);
-    if (params7) {
-        const float* p = params7 + i * 7;
-        e.mass = p[0]; e.inv_m = 1.0f / p[0]; e.ixx = p[1]; e.iyy = p[2]; e.izz = p[3]; e.arm = p[4]; e.ks = p[5]; e.eff = p[6];
+    if (params8) {
+        const float* p = params8 + i * 8;
+        // mass / inertia outside the normal range would break the range-check-free reciprocals of the step: keep the old value
+        const float lo = 1.0e-30f, hi = 1.0e30f;
+        if (p[0] > lo && p[0] < hi) e.mass = p[0];
+        if (p[1] > lo && p[1] < hi) e.ixx = p[1];
+        if (p[2] > lo && p[2] < hi) e.iyy = p[2];
+        if (p[3] > lo && p[3] < hi) e.izz = p[3];
+        e.arm = p[4]; e.ks = p[5]; e.eff = p[6]; e.km = p[7];
     }
-    if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | (((uint32_t)fault2[i * 2 + 1] & FAULT_NEVER) << 2) | (e.fault & LANDED_BIT);
+    if (fault2) e.fault = ((uint32_t)fault2[i * 2] & 3u) | (((uint32_t)fault2[i * 2 + 1] & FAULT_NEVER) << 2) | ((uint32_t)fault2[i * 2 + 1] & LANDED_BIT);
     store_static(pl, i, e);
 }
 
@@ -462,16 +502,7 @@ __global__ void apply_resets_kernel(const DevCfg c, const Planes pl, const int64
         e.fault = (f.x & 3u) | (__umulhi(f.y, (uint32_t)c.max_episode_length) << 2) | landed;
         e.eff = c.fault_eff_lo + c.fault_eff_range * u01(f.z);
     }
-    if (c.dr_enable) {
-        const uint4 a = draw(c.seed, genv, step, P_DR0), b = draw(c.seed, genv, step, P_DR1);
-        e.mass = c.mass * (c.dr_lo + c.dr_range * u01(a.x));
-        e.inv_m = 1.0f / e.mass;
-        e.ixx = c.ixx * (c.dr_lo + c.dr_range * u01(a.y));
-        e.iyy = c.iyy * (c.dr_lo + c.dr_range * u01(a.z));
-        e.izz = c.izz * (c.dr_lo + c.dr_range * u01(a.w));
-        e.arm = c.arm * (c.dr_lo + c.dr_range * u01(b.x));
-        e.ks = 1.0f * (c.dr_lo + c.dr_range * u01(b.y));
-    }
+    if (c.dr_enable) dr_draw_all(e, genv, step, c);
     store_dynamic(pl, i, e);
     store_static(pl, i, e);
 }
@@ -492,7 +523,7 @@ __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     e.ep_ret = 0.0f;
     e.tgt[0] = 0.0f; e.tgt[1] = 0.0f; e.tgt[2] = 1.0f;        // ouzelum.py:71-73
     e.eff = 1.0f;
-    e.mass = c.mass; e.inv_m = 1.0f / c.mass; e.ixx = c.ixx; e.iyy = c.iyy; e.izz = c.izz; e.arm = c.arm; e.ks = 1.0f;
+    e.mass = c.mass; e.ixx = c.ixx; e.iyy = c.iyy; e.izz = c.izz; e.arm = c.arm; e.ks = 1.0f; e.km = c.yaw_km;
     e.fault = FAULT_NEVER << 2;
     store_dynamic(pl, i, e);
     store_static(pl, i, e);
@@ -550,7 +581,16 @@ static void derive_dev_cfg(const ozl_cfg& c, DevCfg& d) {
     d.land_cutoff = c.land_cutoff;
     d.plate_enable = c.plate_enable; d.plate_z = c.plate_z;
     d.plate_r2 = (float)((double)c.plate_radius * (double)c.plate_radius);
-    d.dr_lo = c.dr_lo; d.dr_range = c.dr_range;
+    d.wrench_warmup_steps = c.wrench_warmup_steps;
+    const float nominal[OZL_DR_NUM] = {c.mass, c.ixx, c.iyy, c.izz, c.arm, 1.0f, c.yaw_km};
+    for (int j = 0; j < OZL_DR_NUM; ++j) {
+        const ozl_dr_param& s = c.dr[j];
+        DrSpec& o = d.dr[j];
+        o.dist = s.distribution; o.op = s.operation; o.sched = s.schedule; o.sched_steps = s.schedule_steps;
+        o.a = s.range[0]; o.b = s.range[1]; o.nominal = nominal[j];
+        o.inv_steps = s.schedule_steps > 0 ? 1.0f / (float)s.schedule_steps : 0.0f;          // "1 / sched_step * min(...)"  dr_utils.py:85
+        if (s.distribution == OZL_DR_GAUSSIAN) d.dr_any_gauss = 1;
+    }
     d.flicker_p = (c.pomdp_mode == OZL_POMDP_FLICKER_NOISE) ? 0.1f : c.pomdp_prob;      // POMDP.py:16-18
     const float lo = (float)(1.0 - (double)c.noise_sigma), hi = (float)(1.0 + (double)c.noise_sigma);
     d.noise_lo = lo;
@@ -614,7 +654,12 @@ extern "C" int ozl_cfg_default(ozl_cfg* c, int64_t num_envs) {
     c->arm = (float)arm;
     c->max_angvel = (float)(4.0 * M_PI);
     c->fault_eff_lo = 0.0f; c->fault_eff_range = 0.5f;
-    c->dr_lo = 0.8f; c->dr_range = (float)(1.2 - 0.8);
+    for (int j = 0; j < OZL_DR_NUM; ++j) {       // isaacgymenvs/utils/dr_utils.py:121-130 (scaling, uniform); yaw_km: not randomised
+        c->dr[j].distribution = j == OZL_DR_YAW_KM ? OZL_DR_NONE : OZL_DR_UNIFORM;
+        c->dr[j].operation = OZL_DR_SCALING;
+        c->dr[j].range[0] = 0.8f; c->dr[j].range[1] = 1.2f;
+        c->dr[j].schedule = OZL_DR_SCHED_NONE; c->dr[j].schedule_steps = 0;
+    }
     c->collect_metrics = 1;
     c->plate_enable = 0; c->plate_z = 0.377f; c->plate_radius = 0.35f; c->land_cutoff = 0.0f;
     return 0;
@@ -633,8 +678,19 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
         return set_error("ozl_create: max_episode_length out of range");
     if (cfg->target_period <= 0) return set_error("ozl_create: target_period must be > 0");
     if (cfg->pomdp_mode < 0 || cfg->pomdp_mode > 3) return set_error("ozl_create: unknown pomdp_mode %d", cfg->pomdp_mode);
-    if (!(cfg->mass > 0.f) || !(cfg->ixx > 0.f) || !(cfg->iyy > 0.f) || !(cfg->izz > 0.f))
-        return set_error("ozl_create: mass and inertia must be positive");
+    if (!(cfg->mass > 1e-30f && cfg->mass < 1e30f) || !(cfg->ixx > 1e-30f && cfg->ixx < 1e30f) ||
+        !(cfg->iyy > 1e-30f && cfg->iyy < 1e30f) || !(cfg->izz > 1e-30f && cfg->izz < 1e30f))
+        return set_error("ozl_create: mass and inertia must be positive normal floats");
+    if (cfg->wrench_warmup_steps < 0) return set_error("ozl_create: wrench_warmup_steps must be >= 0");
+    for (int j = 0; j < OZL_DR_NUM; ++j) {
+        const ozl_dr_param& d = cfg->dr[j];
+        if (d.distribution < OZL_DR_NONE || d.distribution > OZL_DR_GAUSSIAN) return set_error("ozl_create: dr[%d].distribution %d unknown", j, d.distribution);
+        if (d.operation != OZL_DR_SCALING && d.operation != OZL_DR_ADDITIVE) return set_error("ozl_create: dr[%d].operation %d unknown", j, d.operation);
+        if (d.schedule < OZL_DR_SCHED_NONE || d.schedule > OZL_DR_SCHED_CONSTANT) return set_error("ozl_create: dr[%d].schedule %d unknown", j, d.schedule);
+        if (d.schedule != OZL_DR_SCHED_NONE && d.schedule_steps <= 0) return set_error("ozl_create: dr[%d].schedule_steps must be > 0", j);
+        if (d.distribution == OZL_DR_LOGUNIFORM && !(d.range[0] > 0.f && d.range[1] > 0.f))
+            return set_error("ozl_create: dr[%d]: loguniform needs a positive range", j);
+    }
     int ndev = 0;
     if (check_cuda(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return 1;
     if (device < 0 || device >= ndev) return set_error("ozl_create: device %d not available (%d visible)", device, ndev);
@@ -703,7 +759,7 @@ static_assert(kStepBlock == kTile, "the step counter retires one work unit per 1
 
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
-                       uint8_t* done_u8 = nullptr, int obs_bulk = 1) {
+                       uint8_t* done_u8 = nullptr, int obs_bulk = 1, int64_t* reset_mirror = nullptr) {
     if (!env) return set_error("%s: env is NULL", who);
     cudaStream_t st = (cudaStream_t)stream;
     if (!actions || !obs || !rew || !reset || !progress) return set_error("%s: NULL buffer", who);
@@ -711,7 +767,7 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
     const int64_t n = env->cfg.num_envs;
     const int64_t full_tiles = n / kTile, tail = n % kTile;
     const int64_t resident = (int64_t)env->sm_count * OZL_TMA_MINB;
-    const bool plain = (target_in == nullptr) && act_mode == ACT_ROTORS && done_u8 == nullptr && obs_bulk;
+    const bool plain = (target_in == nullptr) && act_mode == ACT_ROTORS && done_u8 == nullptr && reset_mirror == nullptr && obs_bulk;
     if (plain && env->tma_min_tiles > 0 && full_tiles >= env->tma_min_tiles &&
         !(((uintptr_t)progress | (uintptr_t)reset) & 15)) {
         // large N: persistent TMA-pipelined kernel over the whole tiles, then one generic block for the ragged tail
@@ -721,15 +777,64 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
                        progress, timeout, ep_ret, full_tiles))
             return check_cuda(cudaGetLastError(), "quad_step_tma_kernel");
         if (tail)
-            quad_step_kernel<kStepBlock><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset, progress,
-                                                                  timeout, ep_ret, nullptr, ACT_ROTORS, nullptr, 1, full_tiles * kTile);
+            quad_step_kernel<kStepBlock, FRONT_NONE><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset,
+                                                                              progress, timeout, ep_ret, nullptr, ACT_ROTORS, nullptr,
+                                                                              nullptr, 1, full_tiles * kTile, FrontArgs{});
         return check_cuda(cudaGetLastError(), "quad_step_kernel(tail)");
     }
-    if (launch_pdl(env, quad_step_kernel<kStepBlock>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev, env->pl,
-                   (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8, obs_bulk,
-                   (int64_t)0))
+    if (launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_NONE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev, env->pl,
+                   (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8, reset_mirror,
+                   obs_bulk, (int64_t)0, FrontArgs{}))
         return check_cuda(cudaGetLastError(), "quad_step_kernel");
     return 0;
+}
+
+// Landing-family steps with the vehicle (and, for LeeLanded, the controller) in the same launch.
+static int launch_front_step(ozl_env* env, int front, const float* actions, const ozl_husky_args* husky, const FrontArgs& fa_in,
+                             float* obs, float* rew, int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream,
+                             const char* who) {
+    if (!env) return set_error("%s: env is NULL", who);
+    if (!husky) return set_error("%s: husky args are NULL", who);
+    if (!obs || !rew || !reset || !progress || (front == FRONT_VEHICLE && !actions)) return set_error("%s: NULL buffer", who);
+    if (((uintptr_t)actions & 15) || ((uintptr_t)obs & 15)) return set_error("%s: actions/obs must be 16-byte aligned", who);
+    FrontArgs fa = fa_in;
+    if (ozl_fill_husky_args(husky, fa.h, who)) return 1;
+    if (!fa.h.tables) return set_error("%s: tables204x2 is NULL", who);
+    if (fa.h.n != env->cfg.num_envs) return set_error("%s: vehicle count %lld != env count %lld", who, (long long)fa.h.n, (long long)env->cfg.num_envs);
+    if (fa.h.reset && fa.h.reset != reset) return set_error("%s: the vehicle and the step must see the same reset buffer", who);
+    fa.h.reset = reset;
+    fa.h.step_ptr = env->pl.ctrl;            // the vehicle follows the handle's device step counter (graph-capturable)
+    const int64_t n = env->cfg.num_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (front == FRONT_VEHICLE)
+        rc = launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_VEHICLE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev,
+                        env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, (const float*)nullptr, (int)ACT_ROTORS,
+                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa);
+    else
+        rc = launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_LEE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev,
+                        env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, (const float*)nullptr, (int)ACT_WRENCH,
+                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa);
+    if (rc) return check_cuda(cudaGetLastError(), who);
+    return 0;
+}
+
+extern "C" int ozl_landing_step(ozl_env* env, const float* actions, const ozl_husky_args* husky, float* obs, float* rew,
+                                int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    return launch_front_step(env, FRONT_VEHICLE, actions, husky, FrontArgs{}, obs, rew, reset, progress, timeout, ep_ret, stream,
+                             "ozl_landing_step");
+}
+
+extern "C" int ozl_lee_landed_step(ozl_env* env, const ozl_lee_landed_args* in, const ozl_husky_args* husky, float* obs, float* rew,
+                                   int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    if (!in || !in->gains16) return set_error("ozl_lee_landed_step: NULL argument");
+    if ((uintptr_t)in->wrench4 & 15) return set_error("ozl_lee_landed_step: wrench4 must be 16-byte aligned");
+    FrontArgs fa{};
+    for (int k = 0; k < 3; ++k) { fa.g.kP[k] = in->gains16[k]; fa.g.kV[k] = in->gains16[3 + k]; fa.g.kR[k] = in->gains16[6 + k]; fa.g.kO[k] = in->gains16[9 + k]; }
+    for (int k = 0; k < 4; ++k) { fa.g.scale[k] = in->gains16[12 + k]; fa.cmd[k] = in->cmd[k]; }
+    fa.mg = in->mg;
+    fa.wrench_out = (float4*)in->wrench4;
+    return launch_front_step(env, FRONT_LEE, nullptr, husky, fa, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_lee_landed_step");
 }
 
 extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* rew, int64_t* reset, int64_t* progress,
@@ -737,18 +842,22 @@ extern "C" int ozl_step(ozl_env* env, const float* actions, float* obs, float* r
     return launch_step(env, actions, nullptr, ACT_ROTORS, obs, rew, reset, progress, timeout, ep_ret, stream, "ozl_step");
 }
 
-extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
-                             int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+static int step_host_impl(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                          int64_t* reset_host, int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
     if (!done_host) return set_error("ozl_step_host: done_host is NULL");
     // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store (measured equal)
     return launch_step(env, actions_host, nullptr, ACT_ROTORS, obs_host, rew_host, reset, progress, timeout, ep_ret, stream,
-                       "ozl_step_host", done_host, 0);
+                       "ozl_step_host", done_host, 0, reset_host);
+}
+extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                             int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
+    return step_host_impl(env, actions_host, obs_host, rew_host, done_host, nullptr, reset, progress, timeout, ep_ret, stream);
 }
 
 extern "C" int ozl_step_host_launch(ozl_env* env, const ozl_host_io* io, void* stream) {
     if (!io) return set_error("ozl_step_host_launch: io is NULL");
-    return ozl_step_host(env, io->actions_host, io->obs_host, io->rew_host, io->done_host, io->reset, io->progress, io->timeout,
-                         io->ep_ret, stream);
+    return step_host_impl(env, io->actions_host, io->obs_host, io->rew_host, io->done_host, io->reset_host, io->reset, io->progress,
+                          io->timeout, io->ep_ret, stream);
 }
 
 extern "C" int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream) {
@@ -801,14 +910,14 @@ extern "C" int ozl_set_state(ozl_env* env, const float* root13, const float* thr
     set_state_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, root13, thrust4, target3, ep_ret);
     return check_cuda(cudaGetLastError(), "set_state_kernel");
 }
-extern "C" int ozl_get_params(ozl_env* env, float* params7, int32_t* fault2, void* stream) {
+extern "C" int ozl_get_params(ozl_env* env, float* params8, int32_t* fault2, void* stream) {
     OZL_ENV_CHECK("ozl_get_params");
-    get_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params7, fault2);
+    get_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params8, fault2);
     return check_cuda(cudaGetLastError(), "get_params_kernel");
 }
-extern "C" int ozl_set_params(ozl_env* env, const float* params7, const int32_t* fault2, void* stream) {
+extern "C" int ozl_set_params(ozl_env* env, const float* params8, const int32_t* fault2, void* stream) {
     OZL_ENV_CHECK("ozl_set_params");
-    set_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params7, fault2);
+    set_params_kernel<<<blocks_for(env->cfg.num_envs, 256), 256, 0, st>>>(env->pl, env->cfg.num_envs, params8, fault2);
     return check_cuda(cudaGetLastError(), "set_params_kernel");
 }
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ void quadcopter_env(const QCfg& c, const uint64_t ste
     int64_t prog = progress[i];
     const bool rst = reset[i] != 0;
     const DevCfg& b = c.body;
-    e.mass = b.mass; e.inv_m = 1.0f / b.mass; e.ixx = b.ixx; e.iyy = b.iyy; e.izz = b.izz; e.arm = 0.f; e.ks = 1.f;
+    e.mass = b.mass; e.ixx = b.ixx; e.iyy = b.iyy; e.izz = b.izz; e.arm = 0.f; e.ks = 1.f; e.km = 0.f;
 
     if (rst) {                                                                        // quadcopter.py:280-299
         const uint4 s0 = draw(c.seed, genv, step, P_SPAWN);
@@ -153,7 +153,8 @@ extern "C" int ozl_quadcopter_step(const ozl_quadcopter_args* a, void* stream) {
     if (!a->actions12 || !a->root13 || !a->dof_pos8 || !a->dof_target8 || !a->thrust4 || !a->obs21 || !a->rew || !a->reset ||
         !a->progress)
         return set_error("ozl_quadcopter_step: NULL buffer");
-    if (a->substeps <= 0 || !(a->mass > 0.f) || !(a->ixx > 0.f) || !(a->iyy > 0.f) || !(a->izz > 0.f))
+    if (a->substeps <= 0 || !(a->mass > 1e-30f && a->mass < 1e30f) || !(a->ixx > 1e-30f && a->ixx < 1e30f) ||
+        !(a->iyy > 1e-30f && a->iyy < 1e30f) || !(a->izz > 1e-30f && a->izz < 1e30f))
         return set_error("ozl_quadcopter_step: bad configuration");
     QCfg c;
     memset(&c, 0, sizeof(c));

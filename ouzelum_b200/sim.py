@@ -109,15 +109,18 @@ class QuadSim:
 
     def get_params(self):
         n = self.num_envs
-        p, f = self._new(n, 7), self._new(n, 2, dtype=torch.int32)
+        p, f = self._new(n, 8), self._new(n, 2, dtype=torch.int32)
         check(lib.ozl_get_params(self._h, p.data_ptr(), f.data_ptr(), _stream()))
         return p, f
 
-    def set_params(self, params7=None, fault2=None):
+    def set_params(self, params8=None, fault2=None):
+        """params8 [N,8] = mass, ixx, iyy, izz, arm, thrust scale, fault effectiveness, yaw_km; fault2 [N,2] = rotor, onset
+        (bit 31 of the onset word carries the env's landed flag, so get_params -> set_params round-trips it)."""
         n = self.num_envs
+        params7 = params8
         if params7 is not None:
             params7 = params7.to(device=self.device, dtype=torch.float32).contiguous()
-            assert tuple(params7.shape) == (n, 7)
+            assert tuple(params7.shape) == (n, 8)
         if fault2 is not None:
             fault2 = fault2.to(device=self.device, dtype=torch.int32).contiguous()
             assert tuple(fault2.shape) == (n, 2)

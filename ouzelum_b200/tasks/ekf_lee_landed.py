@@ -47,13 +47,18 @@ class EKFLeeLanded(_VehicleTargetTask):
 
     def _native_cfg(self):
         # the observation itself also goes through the sensor-fault model env-side (ekf_lee_landed.py:659)
+        # wrench_warmup_steps: during the estimator warm-up the hover force reaches every env and no landing is flagged (:508-529)
         return x500_cfg_from_task(self.cfg, self.num_envs, target_fixed=1, die_z=self.die_z, plate_enable=1,
-                                  plate_z=TARGET_Z, plate_radius=0.35, land_cutoff=self.land_cutoff)
+                                  plate_z=TARGET_Z, plate_radius=0.35, land_cutoff=self.land_cutoff,
+                                  wrench_warmup_steps=int(self.ConvergenceTime))
 
     def create_sim(self):
         super().create_sim()
         n, dev = self.num_envs, self.device
         self.dt = float(self.cfg["sim"]["dt"])
+        # envs of the whole job (all ranks): the reference's shared sensor-trigger counters advance once per env-iteration, so the
+        # fix pattern depends on the TOTAL env count and the global env id, not on how the envs are sharded over GPUs
+        self.num_envs_total = int(self.cfg["env"].get("numEnvsTotal", 0) or n)
         self.ekf = EKFBank(n, frequency=1 / self.dt, device=dev)            # :141
         self.pvfilters = PVFilterBank(n, [1.0, 1.0, 1.0], dev)              # :137: acc_var = 0.01 * 100
         self.controller = Controller(control(), dev)
@@ -85,6 +90,7 @@ class EKFLeeLanded(_VehicleTargetTask):
         a.pos_period, a.pos_phase = (pp if self.attach_pos_sensor else 0), ph
         a.vel_period, a.vel_phase = (vp if self.attach_vel_sensor else 0), vh
         a.per_env_triggers = 1 if self.per_env_triggers else 0
+        a.num_envs_total = self.num_envs_total
         a.acc_var[:] = [1.0, 1.0, 1.0]
         a.pos_var[:] = [0.0000001] * 3
         a.ekf_Dt, a.ekf_g_noise = float(self.ekf.Dt), float(self.ekf.g_noise)
@@ -158,7 +164,7 @@ class EKFLeeLanded(_VehicleTargetTask):
                             gps_data=pos, gps_var=[0.0000001] * 3,                     # :408,430
                             vel_data=vel, vel_var=None,     # the reference's velocity fix runs with R = 0 (PVFilter.py:76-79)
                             trigger=trig,
-                            iter_base=self.sim_step_count * n)   # :417-444
+                            iter_base=self.sim_step_count * self.num_envs_total + self._base)   # :417-444
         check(lib.ozl_waypoint_command(n, self._root.data_ptr(), self.pvfilters._x.data_ptr(), self._target.data_ptr(),
                                        self.target_waypoints.data_ptr(), 1 if warm else 0, self._est.data_ptr(),
                                        self._cmd.data_ptr(), s))                        # :458-503

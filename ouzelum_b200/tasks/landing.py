@@ -6,7 +6,8 @@ Mirrors isaacgymenvs/tasks/lando.py, landing.py and landed.py.  All three share 
   * Landing: the Husky follows lemniscate / circle / square waypoints (landing.py:108-112,208-244,319-364)
   * Landed: evaluation variant -- observation through the sensor-fault model env-side (landed.py:62,340), landing
     detector that cuts thrust within 0.2 m of the target (landed.py:288-295), landing counter (landed.py:265-271)
-One step = one `ozl_husky_step` launch (vehicle + target) followed by one `ozl_step_tracking` launch.
+One step = ONE launch (`ozl_landing_step`: vehicle + target + tracking step per env in one thread); `env.fusedStep = False`
+keeps the two-launch sequence `ozl_husky_step` -> `ozl_step_tracking` for A/B tests (identical bits).
 The PhysX Husky and the leg/plate contact are replaced by a kinematic unicycle and an inelastic plate.
 """
 import torch
@@ -47,6 +48,15 @@ class _VehicleTargetTask(X500Task):
         self.husky.follow_step_counter(ctr.value)
 
     def _launch(self, actions):
+        if self.vehicle_moves and bool(self.cfg["env"].get("fusedStep", True)):
+            import ctypes as C
+            from .._lib import check, lib
+            check(lib.ozl_landing_step(self.sim._h, actions.data_ptr(), C.byref(self.husky._a), self.obs_buf.data_ptr(),
+                                       self.rew_buf.data_ptr(), self.reset_buf.data_ptr(), self.progress_buf.data_ptr(),
+                                       self._timeout_u8.data_ptr(), self.episode_return_buf.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+            self._target = self.husky.target
+            return
         if self.vehicle_moves:
             self._target = self.husky.step(self.reset_buf)
         self.sim.step_tracking(actions, self._target, self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf,

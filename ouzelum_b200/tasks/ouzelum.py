@@ -14,6 +14,59 @@ from ..sim import QuadSim
 from ..vec_task import VecTask
 
 _POMDP = {"none": 0, None: 0, "flicker": 1, "random_noise": 2, "flickering_and_random_noise": 3}
+_DR_DIST = {"uniform": _lib.DR_UNIFORM, "loguniform": _lib.DR_LOGUNIFORM, "gaussian": _lib.DR_GAUSSIAN}
+_DR_OP = {"scaling": _lib.DR_SCALING, "additive": _lib.DR_ADDITIVE}
+_DR_SCHED = {None: _lib.DR_SCHED_NONE, "linear": _lib.DR_SCHED_LINEAR, "constant": _lib.DR_SCHED_CONSTANT}
+# reference attribute names (gymapi.RigidBodyProperties: mass, inertia) and this framework's rotor parameters
+_DR_NAMES = {"mass": "mass", "ixx": "ixx", "iyy": "iyy", "izz": "izz", "arm": "arm", "thrust_scale": "thrust_scale",
+             "yaw_km": "yaw_km", "motor_constant": "yaw_km"}
+
+
+def dr_spec(attr_params):
+    """One attribute block of the reference's `randomization_params` (isaacgymenvs/utils/dr_utils.py:71-81:
+    range / distribution / operation / schedule / schedule_steps) -> ozl_dr_param tuple."""
+    dist, op = attr_params["distribution"], attr_params["operation"]
+    if dist not in _DR_DIST:
+        raise ValueError(f"unknown randomization distribution {dist!r} (uniform, loguniform, gaussian)")
+    if op not in _DR_OP:
+        raise ValueError(f"unknown randomization operation {op!r} (scaling, additive)")
+    sched = attr_params.get("schedule")
+    if sched not in _DR_SCHED:
+        raise ValueError(f"unknown randomization schedule {sched!r} (linear, constant)")
+    lo, hi = attr_params["range"]
+    return (_DR_DIST[dist], _DR_OP[op], float(lo), float(hi), _DR_SCHED[sched], int(attr_params.get("schedule_steps", 0) or 0))
+
+
+def dr_from_task_cfg(cfg):
+    """Domain-randomisation schema of a task dict -> (enable, {parameter: spec}).  Two spellings are accepted:
+      * the reference's: cfg["task"]["randomize"] = True and cfg["task"]["randomization_params"]["actor_params"][<actor>]
+        ["rigid_body_properties" | "rotor_properties"][<attr>] = {range, operation, distribution[, schedule, schedule_steps]}
+        (cfg/task/*.yaml of the stock tasks; applied at resets, tasks/base/vec_task.py:538-768) with attrs
+        mass / ixx / iyy / izz / arm / thrust_scale / yaw_km (alias motor_constant);
+      * the shorthand env["domainRandomization"] = {enable, low, high}: scaling x uniform [low, high) on mass, inertia, arm, thrust scale."""
+    env, task = cfg["env"], cfg.get("task", {}) or {}
+    out = {}
+    short = env.get("domainRandomization", {}) or {}
+    enable = bool(short.get("enable", False))
+    if enable:
+        lo, hi = float(short.get("low", 0.8)), float(short.get("high", 1.2))
+        for name in ("mass", "ixx", "iyy", "izz", "arm", "thrust_scale"):
+            out[name] = (_lib.DR_UNIFORM, _lib.DR_SCALING, lo, hi, 0, 0)
+    if task.get("randomize", False):
+        actors = (task.get("randomization_params", {}) or {}).get("actor_params", {}) or {}
+        if actors and not enable:
+            # the reference randomises only what the YAML lists
+            for name in ("mass", "ixx", "iyy", "izz", "arm", "thrust_scale", "yaw_km"):
+                out[name] = (_lib.DR_NONE, _lib.DR_SCALING, 1.0, 1.0, 0, 0)
+        for actor, props in actors.items():
+            for group in ("rigid_body_properties", "rotor_properties"):
+                for attr, ap in (props.get(group, {}) or {}).items():
+                    if attr not in _DR_NAMES:
+                        raise ValueError(f"randomization_params: attribute {attr!r} of actor {actor!r} is not randomisable here "
+                                         f"(known: {sorted(_DR_NAMES)})")
+                    out[_DR_NAMES[attr]] = dr_spec(ap)
+                    enable = True
+    return enable, out
 
 
 def x500_cfg_from_task(cfg, num_envs, **over):
@@ -21,7 +74,7 @@ def x500_cfg_from_task(cfg, num_envs, **over):
     env, sim = cfg["env"], cfg.get("sim", {})
     dt = float(sim.get("dt", 0.01))
     fault = env.get("rotorFault", {}) or {}
-    dr = env.get("domainRandomization", {}) or {}
+    dr_enable, dr = dr_from_task_cfg(cfg)
     pomdp = env.get("POMDP", "none")
     if pomdp not in _POMDP:
         # isaacgymenvs/utils/POMDP.py:19-20
@@ -38,8 +91,7 @@ def x500_cfg_from_task(cfg, num_envs, **over):
         fault_mode=1 if fault.get("enable", False) else 0,
         fault_eff_lo=float(fault.get("effLow", 0.0)),
         fault_eff_range=float(fault.get("effHigh", 0.5)) - float(fault.get("effLow", 0.0)),
-        dr_enable=1 if dr.get("enable", False) else 0,
-        dr_lo=float(dr.get("low", 0.8)), dr_range=float(dr.get("high", 1.2)) - float(dr.get("low", 0.8)),
+        dr_enable=1 if dr_enable else 0, dr=dr,
         pomdp_mode=_POMDP[pomdp], pomdp_prob=float(env.get("pomdp_prob", 0.0)),
         noise_sigma=float(env.get("pomdp_prob", 0.0)),  # POMDP.py:8-9: one knob feeds both
         collect_metrics=1 if env.get("collectMetrics", True) else 0,
@@ -105,15 +157,16 @@ class X500Task(VecTask):
     # ---- host-consumer step ----------------------------------------------------------------------------------
     def step_host(self, actions_host):
         """`step` for a consumer that lives on the CPU (rl_device == "cpu" in the reference's terms, vec_task.py:353-359):
-        `actions_host` is a pinned [N,4] float32 CPU tensor; returns pinned CPU tensors (obs [N,13], reward [N], done [N] u8)
-        that are valid when the call returns.  The kernel reads / writes them in place across PCIe (zero-copy)."""
+        `actions_host` is a pinned [N,4] float32 CPU tensor; returns pinned CPU tensors (obs [N,13] f32, reward [N] f32,
+        reset [N] int64 -- the reference's dtypes) that are valid when the call returns.  The kernel reads / writes them in place
+        across PCIe (zero-copy).  `host_done_u8` holds the same flags as one byte per env."""
         io = self._host_io.get(actions_host.data_ptr())
         if io is None:
             io = self._make_host_io(actions_host)
         # one foreign call: launch + stream synchronise (ozl_step_host_sync)
         if _lib.lib.ozl_step_host_sync(self.sim._h, io, torch._C._cuda_getCurrentRawStream(self.sim.index)):
             _lib.check(1)
-        return self._h_obs, self._h_rew, self._h_done
+        return self._h_obs, self._h_rew, self._h_reset
 
     def step_host_async(self, actions_host, stream=None):
         """Launch-only half of `step_host` (EnvPool-style pipelining: a CPU consumer that splits its envs over two task objects can
@@ -129,7 +182,12 @@ class X500Task(VecTask):
     def step_host_wait(self):
         if _lib.lib.ozl_stream_sync(self._host_stream):
             _lib.check(1)
-        return self._h_obs, self._h_rew, self._h_done
+        return self._h_obs, self._h_rew, self._h_reset
+
+    @property
+    def host_done_u8(self):
+        """The reset flags of the last host step, one byte per env (pinned CPU tensor)."""
+        return self._h_done
 
     def _make_host_io(self, actions_host):
         """Argument block of ozl_step_host_sync for one actions buffer, validated once and cached by address."""
@@ -139,6 +197,7 @@ class X500Task(VecTask):
             pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()
             self._h_obs, self._h_rew = pin(self.num_envs, self.num_obs), pin(self.num_envs)
             self._h_done = pin(self.num_envs, dt=torch.uint8)
+            self._h_reset = pin(self.num_envs, dt=torch.int64)          # reset_buf in the reference's dtype (vec_task.py:353-359)
         if len(self._host_keep) >= 64:                       # a caller that passes a fresh buffer every step
             self._host_io.clear()
             self._host_keep.clear()
@@ -146,7 +205,7 @@ class X500Task(VecTask):
                 or tuple(actions_host.shape) != (self.num_envs, self.num_acts):
             raise ValueError("step_host needs a contiguous page-locked (pinned) float32 CPU tensor of shape [num_envs, num_acts]")
         io = OzlHostIo(actions_host.data_ptr(), self._h_obs.data_ptr(), self._h_rew.data_ptr(), self._h_done.data_ptr(),
-                       self.reset_buf.data_ptr(), self.progress_buf.data_ptr(), self._timeout_u8.data_ptr(),
+                       self._h_reset.data_ptr(), self.reset_buf.data_ptr(), self.progress_buf.data_ptr(), self._timeout_u8.data_ptr(),
                        self.episode_return_buf.data_ptr())
         ref = C.byref(io)
         self._host_keep.append((io, actions_host))          # keep the struct and the caller's buffer alive

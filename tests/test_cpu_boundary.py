@@ -77,7 +77,7 @@ def test_oracle_constants_agree_with_product(lib):
             continue
         ov = o[k]
         if isinstance(v, tuple):
-            assert tuple(np.float32(ov)) == tuple(np.float32(v)), k
+            assert np.array_equal(np.asarray(ov, np.float32), np.asarray(v, np.float32)), k
         elif isinstance(v, float):
             assert np.float32(ov) == np.float32(v), k
         else:

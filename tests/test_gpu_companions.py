@@ -27,9 +27,21 @@ def test_lee_controller_vs_reference_fixture_and_oracle(name):
     c = Controller(cc, DEV)
     st, cmd = torch.from_numpy(d["state"]).to(DEV), torch.from_numpy(d["command"]).to(DEV)
     thrust, torque = c(st, cmd)
-    # float32 with sin/cos/atan2/asin: 1e-5 relative (abs near 0) against the reference's output
-    np.testing.assert_allclose(thrust.cpu().numpy(), d[name + "_thrust"], rtol=2e-5, atol=2e-5)
-    np.testing.assert_allclose(torque.cpu().numpy(), d[name + "_torque"], rtol=2e-5, atol=5e-5)
+    # float32 with sin/cos/atan2/asin: 1e-5 against the reference's output wherever the state is away from the
+    # singular sets of the Euler extraction (|pitch| -> pi/2: asin' blows up, yaw / roll atan2 degenerate); everywhere else the
+    # looser bound of round 1 holds
+    th, tq = thrust.cpu().numpy(), torque.cpu().numpy()
+    q = d["state"][:, 3:7].astype(np.float64)
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    sin_pitch = 2.0 * (q[:, 3] * q[:, 1] - q[:, 2] * q[:, 0])               # -R[2][0]
+    regular = np.abs(sin_pitch) < 0.95
+    assert regular.mean() > 0.6
+    np.testing.assert_allclose(th[regular], d[name + "_thrust"][regular], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(tq[regular], d[name + "_torque"][regular], rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(d[name + "_torque"]).max()) / 10))
+    np.testing.assert_allclose(th, d[name + "_thrust"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(tq, d[name + "_torque"], rtol=2e-5, atol=5e-5)
+    err = np.abs(tq - d[name + "_torque"])
+    print(name, "max |torque err| regular:", float(err[regular].max()), "all:", float(err.max()), "max |torque|:", float(np.abs(tq).max()))
     t64, q64 = lee_control(d["state"], d["command"], mode={"lee_position_control": 0, "lee_velocity_control": 1,
                                                            "lee_attitude_control": 2}[name], dtype=np.float64)
     np.testing.assert_allclose(thrust.cpu().numpy(), t64, rtol=2e-5, atol=2e-5)
@@ -70,6 +82,40 @@ def test_pv_filter_vs_reference_fixture():
         np.testing.assert_allclose(x, d["states"][t], rtol=3e-3, atol=3e-3 * scale, err_msg=f"t={t}")
         bank.set_states(t_(d["states"][t]))
         bank.set_covariances(t_(d["covs"][t]))
+
+
+def test_pv_filter_float32_error_vs_float64_arbiter():
+    """V2 pin on the GPU (see tests/test_oracle_golden.py::test_pv_filter_float32_error_is_inherent_float64_arbiter): from the
+    reference's own previous state, the kernel's float32 step must be as close to the float64 evaluation as the reference's
+    float32 step is (state and covariance), and must match the reference to 1e-5 where only the prediction runs."""
+    from ouzelum_b200.pv_filter import PVFilterBank
+    from test_oracle_golden import _pv_single_step, pv_fixture_steps
+    d = load("pvfilter.npz")
+    n = d["acc"].shape[1]
+    bank = PVFilterBank(n, [1.0, 1.0, 1.0], DEV)
+    var = [1e-7] * 3
+    t_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    ratios = []
+    for t, ps, pc in pv_fixture_steps(d):
+        bank.set_states(t_(ps))
+        bank.set_covariances(t_(pc))
+        bank.step(accels=t_(d["acc"][t]), orientation=t_(d["quat"][t]), dt=0.01, flip_Qw=(t % 2 == 0),
+                  gps_data=t_(d["pos_meas"][t]), gps_var=var, gps_mask=t_(d["pos_fix"][t]),
+                  vel_data=t_(d["vel_meas"][t]), vel_var=var, vel_mask=t_(d["vel_fix"][t]), vel_var_follows_reference=False)
+        x, P = bank.get_states().cpu().numpy(), bank.get_covariances().cpu().numpy()
+        s64, c64 = _pv_single_step(d, t, ps, pc, np.float64)
+        sref, cref = d["states"][t], d["covs"][t]
+        sc, scc = np.abs(s64).max() + 1.0, np.abs(c64).max()
+        e_ref_s, e_gpu_s = np.abs(sref - s64).max() / sc, np.abs(x - s64).max() / sc
+        e_ref_c, e_gpu_c = np.abs(cref - c64).max() / scc, np.abs(P - c64).max() / scc
+        assert e_gpu_s <= 4.0 * e_ref_s + 2e-7, (t, e_gpu_s, e_ref_s)
+        assert e_gpu_c <= 4.0 * e_ref_c + 2e-7, (t, e_gpu_c, e_ref_c)
+        ratios.append((e_gpu_s / max(e_ref_s, 1e-12), e_gpu_c / max(e_ref_c, 1e-12)))
+        nofix = ~(d["pos_fix"][t] | d["vel_fix"][t])
+        np.testing.assert_allclose(x[nofix], sref[nofix], rtol=1e-5, atol=1e-5 * sc, err_msg=f"predict-only state t={t}")
+        np.testing.assert_allclose(P[nofix], cref[nofix], rtol=1e-5, atol=1e-5 * scc, err_msg=f"predict-only cov t={t}")
+        np.testing.assert_allclose(P, cref, rtol=0, atol=4.0 * e_ref_c * scc + 1e-6 * scc, err_msg=f"cov t={t}")
+    print("GPU / reference float32 error ratios against float64 (state, cov) per step:", [(round(a, 2), round(b, 2)) for a, b in ratios])
 
 
 def test_pv_filter_vs_oracle_single_steps_and_trigger_rule():

@@ -69,7 +69,7 @@ def test_step_fault_dr_noise_bit_exact():
         ora.step(a)
         _compare(sim, ora, b, f"t={t}")
     p, f = sim.get_params()
-    assert torch.equal(p[:, :6].cpu(), ora.params)
+    assert torch.equal(p[:, :6].cpu(), ora.params[:, :6]) and torch.equal(p[:, 7].cpu(), ora.params[:, 6])
     assert torch.equal(p[:, 6].cpu(), ora.fault_eff)
     assert torch.equal(f[:, 0].cpu().long(), ora.fault_rotor)
     assert torch.equal(f[:, 1].cpu().long(), ora.fault_onset)

@@ -266,8 +266,9 @@ def test_step_host_zero_copy_matches_device_step():
         a = (torch.rand(n, 4, generator=g) * 2 - 1).pin_memory()
         o1, r1, d1, _ = e1.step(a.to(DEV))
         ho, hr, hd = e2.step_host(a)
-        assert not ho.is_cuda and ho.is_pinned()
-        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu().to(torch.uint8), hd), t
+        assert not ho.is_cuda and ho.is_pinned() and hd.dtype == torch.int64          # the reference's dtypes on the host side too
+        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu(), hd), t
+        assert torch.equal(d1.cpu().to(torch.uint8), e2.host_done_u8), t
     assert torch.equal(e1.reset_buf, e2.reset_buf) and torch.equal(e1.progress_buf, e2.progress_buf)
     with pytest.raises(ValueError):
         e2.step_host(torch.zeros(n, 4))          # not pinned
@@ -279,7 +280,7 @@ def test_step_host_zero_copy_matches_device_step():
         o1, r1, d1, _ = e1.step(a.to(DEV))
         e2.step_host_async(a, side)
         ho, hr, hd = e2.step_host_wait()
-        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu().to(torch.uint8), hd), t
+        assert torch.equal(o1["obs"].cpu(), ho) and torch.equal(r1.cpu(), hr) and torch.equal(d1.cpu(), hd), t
     assert e1.sim.step_count == e2.sim.step_count == 80
 
 
@@ -645,3 +646,71 @@ def test_reset_idx_and_reset_done_surface():
         assert -1.5 <= pos[i, 0] <= 1.5 and -1.5 <= pos[i, 1] <= 1.5 and 0.75 <= pos[i, 2] <= 2.55      # spawn box, one free-fall step
         assert float(thrust[i].abs().max()) == 0.0                                                 # ouzelum.py:247-248
     assert float(thrust[0].min()) > 0.0
+
+
+@pytest.mark.parametrize("task", ["Landing", "Landed"])
+def test_landing_one_launch_step_equals_two_launch_sequence(task):
+    """`ozl_landing_step` (vehicle + tracking step in ONE launch, what Landing / Landed use) against the two-launch sequence
+    ozl_husky_step -> ozl_step_tracking: same device functions, no FMA contraction anywhere => identical bits."""
+    import ouzelum_b200
+    n = 3001
+    mk = lambda fused: ouzelum_b200.make(seed=13, task=task, num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                         cfg=ouzelum_b200.task_config(task, n, seed=13, maxEpisodeLength=45, fusedStep=fused,
+                                                                      rotorFault={"enable": True}))
+    e1, e2 = mk(True), mk(False)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    for t in range(120):
+        a = torch.rand(n, 4, device=DEV, generator=g) * 2 - 1
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a.clone())
+        assert torch.equal(o1["obs"], o2["obs"]) and torch.equal(r1, r2) and torch.equal(d1, d2), t
+        assert torch.equal(e1.husky.pose, e2.husky.pose) and torch.equal(e1.husky.idx, e2.husky.idx), t
+    assert torch.equal(e1.root_states, e2.root_states) and torch.equal(e1.target_root_positions, e2.target_root_positions)
+    assert e1.sim.step_count == e2.sim.step_count == 120 and int(e1.metrics()[9]) > 0
+    assert torch.equal(e1.metrics(), e2.metrics())
+
+
+def test_lee_landed_one_launch_step_vs_chain_and_oracle():
+    """`ozl_lee_landed_step` (vehicle + Lee controller + detector + physics in ONE launch) against (a) the launch chain
+    vehicle -> apply_resets -> get_state -> ozl_lee_wrench -> ozl_step_wrench and (b) the oracles: controller on the state after
+    reset_idx (lee_landed.py:267-270,311), force zeroed for just-reset envs but NOT the torque (:324-325), force and torque
+    zeroed within 0.2 m of the CONTROLLER target (:305,318-322)."""
+    import ouzelum_b200
+    from oracle.lee_control import lee_control
+    from oracle.quad_step import QuadStepOracle
+    n = 2000
+    mk = lambda fused: ouzelum_b200.make(seed=17, task="LeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+                                         cfg=ouzelum_b200.task_config("LeeLanded", n, seed=17, maxEpisodeLength=60, fusedStep=fused))
+    e1, e2 = mk(True), mk(False)
+    phys = QuadStepOracle(e1.native_cfg.to_dict())
+    a = torch.zeros(n, 4, device=DEV)
+    flips = 0
+    for t in range(150):
+        st = e1.sim.get_state()
+        e2.sim.set_state(root=st["root"], thrust=st["thrust"], target=st["target"], ep_ret=st["ep_ret"])
+        e2.husky.pose.copy_(e1.husky.pose), e2.husky.idx.copy_(e1.husky.idx)
+        e2.reset_buf.copy_(e1.reset_buf), e2.progress_buf.copy_(e1.progress_buf)
+        params, fault = e1.sim.get_params()
+        phys.load(st["root"].cpu().numpy(), st["thrust"].cpu().numpy(), st["target"].cpu().numpy(), st["ep_ret"].cpu().numpy(),
+                  params.cpu().numpy(), fault.cpu().numpy(), e1.reset_buf.cpu().numpy(), e1.progress_buf.cpu().numpy(), t)
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        # (a) chain: same device functions; the chain's detector uses torch's norm, so a flag may flip exactly at the 0.2 m threshold
+        same = (o1["obs"] == o2["obs"]).all(dim=1) & (r1 == r2) & (d1 == d2)
+        flips += int((~same).sum())
+        far = (e2._root[:, 0:3] - torch.tensor([0.0, 0.0, 1.0], device=DEV)).norm(dim=1) > 0.21   # chain wrench is stored AFTER the zeroing
+        assert torch.equal(e1._wrench[far], e2._wrench[far]), t
+        # (b) oracle: controller on the post-reset state, then the wrench step with the detector on the controller target
+        root = phys.post_reset_root().numpy()
+        cmd = np.tile(np.array([[0.0, 0.0, 1.0, 0.0]], np.float32), (n, 1))
+        th, tq = lee_control(root, cmd, mode=0)
+        w = e1._wrench.cpu().numpy()
+        np.testing.assert_allclose(w[:, 0], np.float32(2 * 9.81) * th, rtol=2e-5, atol=2e-4, err_msg=f"thrust t={t}")
+        np.testing.assert_allclose(w[:, 1:], tq, rtol=2e-5, atol=1e-4, err_msg=f"torque t={t}")
+        tgt = e1.husky.target.cpu()
+        obs_o, rew_o, reset_o, _ = phys.step(torch.from_numpy(w), target_in=tgt, act_mode=1,
+                                             det_target=torch.tensor([0.0, 0.0, 1.0]))
+        assert torch.equal(o1["obs"].cpu(), obs_o) and torch.equal(r1.cpu(), rew_o) and torch.equal(d1.cpu(), reset_o), t
+        assert torch.equal(e1.root_states.cpu(), phys.root), t
+    assert flips <= 4, flips
+    assert int(e1.metrics()[9]) > 0 and int(e1.metrics()[2]) > 0          # episodes ended, some of them after reaching the hover point

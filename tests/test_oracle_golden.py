@@ -98,6 +98,59 @@ def test_pv_filter_matches_reference_class():
         bank.state, bank.cov = d["states"][t].copy(), d["covs"][t].copy()
 
 
+def _pv_single_step(d, t, prev_state, prev_cov, dtype):
+    """One reference-ordered PV step (predict, gated position fix, gated velocity fix -- ekf_lee_landed.py:419-440) of the
+    oracle in `dtype`, from the given state."""
+    from oracle.pv_filter import PVFilterBank
+    n = d["acc"].shape[1]
+    b = PVFilterBank(n, [1.0, 1.0, 1.0], dtype=dtype)
+    b.state, b.cov = prev_state.astype(dtype).copy(), prev_cov.astype(dtype).copy()
+    var = np.full(3, 0.0000001, dtype)
+    b.prediction_step(d["acc"][t], d["quat"][t], 0.01, flip_Qw=(t % 2 == 0))
+    if d["pos_fix"][t].any():
+        b.correction_step(gps_data=d["pos_meas"][t], gps_var=var, mask=d["pos_fix"][t])
+    if d["vel_fix"][t].any():
+        b.correction_step(vel_data=d["vel_meas"][t], vel_var=var, mask=d["vel_fix"][t])
+    return b.state, b.cov
+
+
+def pv_fixture_steps(d):
+    """(t, previous state, previous covariance) of the reference run stored in pvfilter.npz: every step is evaluated from the
+    REFERENCE's own previous state, so errors do not accumulate across steps."""
+    n = d["acc"].shape[1]
+    s, c = np.zeros((n, 9), np.float32), np.broadcast_to(np.eye(9, dtype=np.float32) * 1000, (n, 9, 9)).copy()
+    for t in range(d["acc"].shape[0]):
+        yield t, s, c
+        s, c = d["states"][t], d["covs"][t]
+
+
+def test_pv_filter_float32_error_is_inherent_float64_arbiter():
+    """V2 pin.  The float32 Kalman update with P = 1000 I and R = 1e-7 (R = 0 in the velocity fix) is ill-conditioned, so two
+    correct float32 implementations differ by far more than 1e-5.  Arbiter: the same step evaluated in float64.  The oracle's
+    float32 error against it must be no larger than a small multiple of the REFERENCE's own float32 error (the fixture is the
+    reference's float32 output) -- for the state AND for the covariance -- and where no fix fires (prediction only,
+    PVFilter.py:25-64) the oracle must match the reference to 1e-5."""
+    d = load("pvfilter.npz")
+    worst = 0.0
+    for t, ps, pc in pv_fixture_steps(d):
+        s32, c32 = _pv_single_step(d, t, ps, pc, np.float32)
+        s64, c64 = _pv_single_step(d, t, ps, pc, np.float64)
+        sref, cref = d["states"][t], d["covs"][t]
+        sc, scc = np.abs(s64).max() + 1.0, np.abs(c64).max()
+        e_ref_s, e_ora_s = np.abs(sref - s64).max() / sc, np.abs(s32 - s64).max() / sc
+        e_ref_c, e_ora_c = np.abs(cref - c64).max() / scc, np.abs(c32 - c64).max() / scc
+        assert e_ora_s <= 4.0 * e_ref_s + 2e-7, (t, e_ora_s, e_ref_s)
+        assert e_ora_c <= 4.0 * e_ref_c + 2e-7, (t, e_ora_c, e_ref_c)
+        worst = max(worst, e_ref_s, e_ref_c)
+        nofix = ~(d["pos_fix"][t] | d["vel_fix"][t])
+        assert nofix.any()
+        np.testing.assert_allclose(s32[nofix], sref[nofix], rtol=1e-5, atol=1e-5 * sc, err_msg=f"predict-only state t={t}")
+        np.testing.assert_allclose(c32[nofix], cref[nofix], rtol=1e-5, atol=1e-5 * scc, err_msg=f"predict-only cov t={t}")
+        # the stored covariances are now asserted against, not only used to re-synchronise
+        np.testing.assert_allclose(c32, cref, rtol=0, atol=4.0 * e_ref_c * scc + 1e-6 * scc, err_msg=f"cov t={t}")
+    assert worst > 1e-6          # the reference itself is >= 1e-5-ish away from float64 on the fix steps: 1e-5 parity is not attainable
+
+
 def test_pv_filter_known_answer_from_survey():
     from oracle.pv_filter import PVFilterBank
     d = load("pvfilter.npz")
