@@ -35,27 +35,52 @@ class RecurrentActor(nn.Module):
         z = torch.zeros(self.lstm.num_layers, num_envs, self.lstm.hidden_size, device=device)
         return z, z.clone()
 
-    def forward(self, obs, lstm_state, done, action=None):
-        """One time step for every env (the collection path of model.py:35-68)."""
+    def get_states(self, obs, lstm_state, done):
+        """model.py:35-53: MLP, then the LSTM over the leading time axis ([T*B, obs] with B = lstm_state batch), state zeroed
+        where `done`.  The cell is written as two GEMMs + pointwise on the nn.LSTM's own parameters: cuDNN's persistent RNN kernel
+        needs 8.4 ms for (seq 1, batch 32768, hidden 128) on B200, the GEMM form 0.2 ms (profiles/r01_configs.md)."""
         x = self.network(obs)
-        keep = (1.0 - done).view(-1, 1)
-        h0, c0 = keep * lstm_state[0][0], keep * lstm_state[1][0]
-        # single-step LSTM cell written as two GEMMs + pointwise on the nn.LSTM's own parameters: cuDNN's persistent RNN
-        # kernel needs 8.4 ms for (seq 1, batch 32768, hidden 128) on B200, the GEMM form 0.2 ms (profiles/r01_configs.md)
+        batch = lstm_state[0].shape[1]
+        x = x.reshape(-1, batch, self.lstm.input_size)
+        done = done.reshape(-1, batch)
         L = self.lstm
-        gates = torch.addmm(L.bias_ih_l0 + L.bias_hh_l0, x, L.weight_ih_l0.t()).addmm_(h0, L.weight_hh_l0.t())
-        i, f, g, o = gates.chunk(4, dim=1)
-        c1 = torch.sigmoid(f) * c0 + torch.sigmoid(i) * torch.tanh(g)
-        h1 = torch.sigmoid(o) * torch.tanh(c1)
-        lstm_state = (h1.unsqueeze(0), c1.unsqueeze(0))
-        mean = self.actor_mean(h1)
-        std = torch.exp(self.actor_logstd.expand_as(mean))
+        bias = L.bias_ih_l0 + L.bias_hh_l0
+        h, c = lstm_state[0][0], lstm_state[1][0]
+        out = []
+        for xt, dt in zip(x, done):
+            keep = (1.0 - dt).view(-1, 1)
+            h, c = keep * h, keep * c
+            gates = torch.addmm(bias, xt, L.weight_ih_l0.t()).addmm_(h, L.weight_hh_l0.t())
+            i, f, g, o = gates.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out.append(h)
+        hidden = out[0] if len(out) == 1 else torch.cat(out, 0)
+        return hidden, (h.unsqueeze(0), c.unsqueeze(0))
+
+    def distribution(self, obs, lstm_state, done):
+        """(action mean, action std, new LSTM state) of the Normal policy (model.py:56-59)."""
+        hidden, lstm_state = self.get_states(obs, lstm_state, done)
+        mean = self.actor_mean(hidden)
+        return mean, torch.exp(self.actor_logstd.expand_as(mean)), lstm_state
+
+    @staticmethod
+    def log_prob_entropy(mean, std, action):
+        """Normal(mean, std).log_prob(action).sum(1) and .entropy().sum(1) (model.py:67)."""
+        logp = (-((action - mean) ** 2) / (2 * std * std) - torch.log(std) - 0.5 * math.log(2 * math.pi)).sum(1)
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).sum(1)
+        return logp, ent
+
+    def forward(self, obs, lstm_state, done, action=None):
+        """model.py:55-68, same signature and return: (action, log-prob, entropy, lstm_state).  With `action` given (the update
+        path) the mean is perturbed by U(-alpha, alpha) -- RPO -- on the module's own device (the reference hard-codes "cuda:0")."""
+        mean, std, lstm_state = self.distribution(obs, lstm_state, done)
         if action is None:
             action = mean + std * torch.randn_like(mean)
         else:
             mean = mean + (torch.rand_like(mean) * 2 - 1) * self.rpo_alpha
-        logp = (-((action - mean) ** 2) / (2 * std * std) - torch.log(std) - 0.5 * math.log(2 * math.pi)).sum(1)
-        return action, logp, lstm_state
+        logp, ent = self.log_prob_entropy(mean, std, action)
+        return action, logp, ent, lstm_state
 
 
 class RolloutStorage:
@@ -76,7 +101,7 @@ def collect_rollout(env, actor, storage, state, pomdp=None):
     next_obs, pomdp_obs, next_done, lstm_state = state["next_obs"], state["pomdp_obs"], state["next_done"], state["lstm_state"]
     for t in range(steps):
         storage.obs[t], storage.pomdps[t], storage.dones[t] = next_obs, pomdp_obs, next_done
-        action, logp, lstm_state = actor(pomdp_obs, lstm_state, next_done)
+        action, logp, _, lstm_state = actor(pomdp_obs, lstm_state, next_done)
         storage.actions[t], storage.logprobs[t] = action, logp
         obs_dict, rew, done, _ = env.step(action)
         next_obs = obs_dict["obs"]

@@ -176,6 +176,24 @@ class EKFLeeLanded(_VehicleTargetTask):
                              self._timeout_u8, self.episode_return_buf)
         self.sim_step_count += 1
 
+    # ---- checkpoint / resume: filter banks and glue buffers are part of the env state
+    def state_dict(self):
+        sd = super().state_dict()
+        sd.update(ekf_q=self.ekf._q.cpu(), ekf_P=self.ekf._P.cpu(), pv_x=self.pvfilters._x.cpu(), pv_P=self.pvfilters._P.cpu(),
+                  prev_root_linvels=self.prev_root_linvels.cpu(), target_waypoints=self.target_waypoints.cpu(),
+                  sim_step_count=int(self.sim_step_count))
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        self.ekf._q.copy_(sd["ekf_q"])
+        self.ekf._P.copy_(sd["ekf_P"])
+        self.pvfilters._x.copy_(sd["pv_x"])
+        self.pvfilters._P.copy_(sd["pv_P"])
+        self.prev_root_linvels.copy_(sd["prev_root_linvels"])
+        self.target_waypoints.copy_(sd["target_waypoints"])
+        self.sim_step_count = int(sd["sim_step_count"])
+
     @property
     def landings(self):
         return int(self.sim.metrics()[2].item())

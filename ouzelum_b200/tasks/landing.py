@@ -66,6 +66,21 @@ class _VehicleTargetTask(X500Task):
     def husky_positions(self):
         return self.husky.husky_positions
 
+    # ---- checkpoint / resume: the vehicle is part of the env state
+    def state_dict(self):
+        sd = super().state_dict()
+        sd.update(husky_pose=self.husky.pose.cpu(), husky_idx=self.husky.idx.cpu(), husky_target=self.husky.target.cpu(),
+                  husky_step_count=int(self.husky.step_count))
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        self.husky.pose.copy_(sd["husky_pose"])
+        self.husky.idx.copy_(sd["husky_idx"])
+        self.husky.target.copy_(sd["husky_target"])
+        self.husky.step_count = int(sd["husky_step_count"])
+        self._target = self.husky.target
+
 
 class Lando(_VehicleTargetTask):
     """isaacgymenvs/tasks/lando.py: the Husky is driven with constant opposing wheel targets (lando.py, create_envs:

@@ -258,7 +258,8 @@ class X500Task(VecTask):
         return {"root": st["root"].cpu(), "thrust": st["thrust"].cpu(), "target": st["target"].cpu(), "ep_ret": st["ep_ret"].cpu(),
                 "params": params.cpu(), "fault": fault.cpu(), "step_count": self.sim.step_count,
                 "reset_buf": self.reset_buf.cpu(), "progress_buf": self.progress_buf.cpu(), "obs_buf": self.obs_buf.cpu(),
-                "rew_buf": self.rew_buf.cpu(), "seed": int(self.native_cfg.seed), "num_envs": self.num_envs}
+                "rew_buf": self.rew_buf.cpu(), "timeout_buf": self._timeout_u8.cpu(), "episode_return_buf": self.episode_return_buf.cpu(),
+                "seed": int(self.native_cfg.seed), "num_envs": self.num_envs, "task": type(self).__name__}
 
     def load_state_dict(self, sd):
         if sd["num_envs"] != self.num_envs:
@@ -272,6 +273,11 @@ class X500Task(VecTask):
         self.progress_buf.copy_(sd["progress_buf"])
         self.obs_buf.copy_(sd["obs_buf"])
         self.rew_buf.copy_(sd["rew_buf"])
+        if "timeout_buf" in sd:
+            self._timeout_u8.copy_(sd["timeout_buf"])
+            self.episode_return_buf.copy_(sd["episode_return_buf"])
+        if sd.get("task", type(self).__name__) != type(self).__name__:
+            raise ValueError(f"checkpoint of task {sd['task']!r} loaded into {type(self).__name__!r}")
         self._graph = None
 
     def metrics(self, clear=False):

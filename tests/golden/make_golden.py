@@ -253,6 +253,37 @@ def main():
                                             "min_dist", "x0", "y0", "z0"]),
                         landing_counter=counter)
     made.append("landed_logs.npz")
+
+    # ---------------------------------------------------------------- RPO-LSTM Actor (config 5 / SURVEY 8f rank 1)
+    # the reference's own module (RPO-LSTM/model.py:11-68), unmodified, on CPU: weights after ITS initialisation, a 3-step sequence
+    # through get_states / forward (action=None: the collection path; the update path hard-codes "cuda:0", model.py:65)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_rpo_lstm_model", os.path.join(PKG, "RPO-LSTM", "model.py"))
+    ref_model = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_model)
+
+    class _Space:
+        def __init__(self, *shape):
+            self.shape = shape
+    torch.manual_seed(1234)
+    actor = ref_model.Actor(_Space(13), _Space(4))
+    with torch.no_grad():
+        actor.actor_logstd.copy_(torch.tensor([[-0.3, 0.1, 0.0, 0.4]]))       # a trained-looking log-std, so that entropy / log-prob are not trivial
+    B, T = 7, 3
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randn(T * B, 13, generator=g)
+    done = (torch.rand(T * B, generator=g) < 0.3).float()
+    h0, c0 = torch.randn(1, B, 128, generator=g) * 0.5, torch.randn(1, B, 128, generator=g) * 0.5
+    torch.manual_seed(99)
+    with torch.no_grad():
+        # one step (collection, main.py:95) and a T-step sequence (update path shapes, agent.py:95-100)
+        a1, lp1, en1, (h1, c1) = actor(obs[:B], (h0, c0), done[:B])
+        aT, lpT, enT, (hT, cT) = actor(obs, (h0, c0), done)
+    sd = {"sd__" + k: v.numpy() for k, v in actor.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "rpo_lstm_actor.npz"), obs=obs.numpy(), done=done.numpy(), h0=h0.numpy(), c0=c0.numpy(),
+                        a1=a1.numpy(), lp1=lp1.numpy(), en1=en1.numpy(), h1=h1.numpy(), c1=c1.numpy(),
+                        aT=aT.numpy(), lpT=lpT.numpy(), enT=enT.numpy(), hT=hT.numpy(), cT=cT.numpy(), **sd)
+    made.append("rpo_lstm_actor.npz")
     print("wrote", made)
 
 

@@ -143,11 +143,39 @@ def test_recurrent_actor_cell_equals_nn_lstm():
     obs, done = torch.randn(n, 13), (torch.rand(n) < 0.3).float()
     st = (torch.randn(1, n, 128), torch.randn(1, n, 128))
     with torch.no_grad():
-        act, logp, s1 = a(obs, st, done)
+        act, logp, ent, s1 = a(obs, st, done)
         keep = (1 - done).view(1, -1, 1)
         _, s2 = a.lstm(a.network(obs).unsqueeze(0), (keep * st[0], keep * st[1]))
-    assert act.shape == (n, 4) and logp.shape == (n,)
+    assert act.shape == (n, 4) and logp.shape == (n,) and ent.shape == (n,)
     assert (s1[0] - s2[0]).abs().max() < 1e-5 and (s1[1] - s2[1]).abs().max() < 1e-5
+
+
+def test_recurrent_actor_equals_reference_actor_fixture():
+    """(f)1: `RecurrentActor` against the reference's UNMODIFIED `RPO-LSTM/model.py` Actor (tests/golden/rpo_lstm_actor.npz, made
+    by running that module on CPU): it must LOAD the reference's state dict (the `<tag>_actor` checkpoint format of
+    RPO-LSTM/agent.py:136-147) and reproduce log-prob, entropy and LSTM state of a single step and of a 3-step sequence to 1e-6."""
+    import os
+    import torch
+    from ouzelum_b200.rollout import RecurrentActor
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpo_lstm_actor.npz"))
+    sd = {k[4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd__")}
+    a = RecurrentActor()
+    assert set(sd) == set(a.state_dict())                       # same parameter names and shapes as the reference module
+    a.load_state_dict(sd, strict=True)
+    t = lambda k: torch.from_numpy(d[k])
+    B = d["h0"].shape[1]
+    with torch.no_grad():
+        for tag, obs, done in (("1", t("obs")[:B], t("done")[:B]), ("T", t("obs"), t("done"))):
+            mean, std, (h, c) = a.distribution(obs, (t("h0"), t("c0")), done)
+            logp, ent = a.log_prob_entropy(mean, std, t("a" + tag))          # the reference's sampled action under OUR distribution
+            torch.testing.assert_close(logp, t("lp" + tag), rtol=1e-6, atol=2e-6)
+            torch.testing.assert_close(ent, t("en" + tag), rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(h, t("h" + tag), rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(c, t("c" + tag), rtol=1e-6, atol=1e-6)
+        # forward() has the reference's signature and return tuple: (action, log-prob, entropy, lstm_state)
+        act, lp, en, st = a(t("obs")[:B], (t("h0"), t("c0")), t("done")[:B], action=t("a1"))
+        assert act.shape == (B, 4) and lp.shape == (B,) and en.shape == (B,) and st[0].shape == (1, B, 128)
+        torch.testing.assert_close(en, t("en1"), rtol=1e-6, atol=1e-6)
 
 
 def test_c_abi_argument_errors_need_no_gpu(lib):
