@@ -6,7 +6,10 @@
 //   * the step index, warm-up flag and the shared sensor-trigger counters come from the env's DEVICE step counter, so the
 //     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
 //   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
+#ifndef OZL_FUSED_PHILOX_INLINE
 #define OZL_PHILOX_NOINLINE 1
+#endif
+#include <cstdlib>
 #include "internal.h"
 #include "bulk_copy.cuh"
 #include "quad_io.cuh"
@@ -37,15 +40,9 @@ struct EkfLeeArgs {
     LeeGains g;
 };
 
-#ifndef OZL_EKF_BLOCK
-#define OZL_EKF_BLOCK 128
-#endif
-#ifndef OZL_EKF_MINB
-#define OZL_EKF_MINB 4
-#endif
-constexpr int kEkfBlock = OZL_EKF_BLOCK;
-static_assert(kEkfBlock % kTile == 0, "a block covers whole 128-env tiles: one step-counter work unit per tile (step_counter.cuh)");
-static_assert(kEkfBlock >= 96, "the 81 plane copies of the covariance tile are issued by 81 different threads");
+// Envs per CTA: 128 (4 CTAs / SM), 256 (2) or 512 (1).  All give the same 512 resident env-threads per SM at 128 registers; the
+// larger blocks keep more warps in the same phase of this long kernel (see ozl_ekf_lee_block()).
+constexpr int ekf_minb(int block) { return block <= 128 ? 4 : (block <= 256 ? 2 : 1); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -70,10 +67,11 @@ struct StepIo {
     float* obs; float* rew; int64_t* reset; int64_t* progress; uint8_t* timeout; float* ep_ret;
 };
 
-template <bool WITH_STEP>
-__global__ void __launch_bounds__(kEkfBlock, OZL_EKF_MINB)
+template <int kEkfBlock, bool WITH_STEP>
+__global__ void __launch_bounds__(kEkfBlock, ekf_minb(kEkfBlock))
 ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma, const HuskyArgs h, const StepIo io) {
-    __shared__ __align__(128) float s_P[81 * kEkfBlock];
+    static_assert(kEkfBlock >= 96 && kEkfBlock % 32 == 0, "the 81 plane copies of the covariance tile are issued by 81 different threads");
+    extern __shared__ __align__(128) float s_P[];            // [81][kEkfBlock] covariance tile, later the [kEkfBlock][13] observation tile
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint64_t s_step;
     const int tid = threadIdx.x;
@@ -269,13 +267,29 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             for (int k = tid; k < nflt; k += kEkfBlock) dst[k] = s_obs[k];
         }
     }
-    block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, (unsigned long long)((n_here + kTile - 1) / kTile) + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
+    // step counter: the launch retires one unit per 128-env tile in total -- block b accounts for the tiles that END in its env range
+    const unsigned long long units = (unsigned long long)((base + n_here + kTile - 1) / kTile - (base + kTile - 1) / kTile);
+    block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, units + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
     if (tid == 0) bulk_wait_read_all();
 }
 
 }  // namespace ozl
 
 using namespace ozl;
+
+// Envs per CTA of the fused kernel.  Every choice keeps 512 env-threads resident per SM; OZL_EKF_BLOCK (128 / 256 / 512) overrides
+// the default for experiments.
+static int ozl_ekf_lee_block(const ozl_env* env, int64_t n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* v = getenv("OZL_EKF_BLOCK");
+        forced = v ? atoi(v) : 0;
+        if (forced != 0 && forced != 128 && forced != 256 && forced != 512) forced = 0;
+    }
+    if (forced) return forced;
+    (void)env; (void)n;
+    return 128;
+}
 
 static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_husky_args* husky, const StepIo io, void* stream) {
     if (!env || !in) return set_error("ozl_ekf_lee_step: NULL argument");
@@ -305,9 +319,8 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
     // TMA path: every [k][N] plane slice of a block must start on a 16-byte boundary and be a multiple of 16 bytes long
     const int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);
-    const unsigned grid = (unsigned)((a.n + kEkfBlock - 1) / kEkfBlock);
+    HuskyArgs h{};
     if (husky) {
-        HuskyArgs h;
         if (ozl_fill_husky_args(husky, h, "ozl_ekf_lee_landed_step")) return 1;
         if (!h.tables) return set_error("ozl_ekf_lee_landed_step: tables204x2 is NULL");
         if (h.n != a.n) return set_error("ozl_ekf_lee_landed_step: vehicle count %lld != env count %lld", (long long)h.n, (long long)a.n);
@@ -315,13 +328,29 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
         if ((uintptr_t)io.obs & 15) return set_error("ozl_ekf_lee_landed_step: obs must be 16-byte aligned");
         if (io.reset != a.reset || (h.reset && h.reset != a.reset))
             return set_error("ozl_ekf_lee_landed_step: the estimator, the vehicle and the step must see the same reset buffer");
-        if (launch_pdl(env, ekf_lee_fused_kernel<true>, dim3(grid), dim3(kEkfBlock), (cudaStream_t)stream, env->dev, env->pl, a, use_tma, h, io))
-            return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
-    } else {
-        if (launch_pdl(env, ekf_lee_fused_kernel<false>, dim3(grid), dim3(kEkfBlock), (cudaStream_t)stream, env->dev, env->pl, a, use_tma,
-                       HuskyArgs{}, io))
-            return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
     }
+    const int block = ozl_ekf_lee_block(env, a.n);
+    const unsigned grid = (unsigned)((a.n + block - 1) / block);
+    const size_t smem = (size_t)81 * block * sizeof(float);
+    int rc;
+#define OZL_LAUNCH_EKF(B, WS)                                                                                                   \
+    do {                                                                                                                        \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            if (check_cuda(cudaFuncSetAttribute(ekf_lee_fused_kernel<B, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                                81 * B * (int)sizeof(float)), "cudaFuncSetAttribute")) return 1;               \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        rc = launch_pdl_smem(env, ekf_lee_fused_kernel<B, WS>, dim3(grid), dim3(B), smem, (cudaStream_t)stream, env->dev,       \
+                             env->pl, a, use_tma, h, io);                                                                       \
+    } while (0)
+    if (husky) {
+        if (block == 512) OZL_LAUNCH_EKF(512, true); else if (block == 256) OZL_LAUNCH_EKF(256, true); else OZL_LAUNCH_EKF(128, true);
+    } else {
+        if (block == 512) OZL_LAUNCH_EKF(512, false); else if (block == 256) OZL_LAUNCH_EKF(256, false); else OZL_LAUNCH_EKF(128, false);
+    }
+#undef OZL_LAUNCH_EKF
+    if (rc) return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
     return 0;
 }
 

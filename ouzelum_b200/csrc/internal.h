@@ -73,6 +73,18 @@ struct ozl_env {
 // consecutive steps on a stream are strictly dependent, but the NEXT step's blocks can be made resident and parked in
 // griddep_wait() while the current step drains, which takes the launch latency off the critical path of short steps.
 template <typename... KArgs, typename... Args>
+static inline int launch_pdl_smem(ozl_env* env, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env->use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...) != cudaSuccess;
+}
+template <typename... KArgs, typename... Args>
 static inline int launch_pdl(ozl_env* env, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
