@@ -224,9 +224,11 @@ def run_ours(args):
     import ouzelum_b200
     from ouzelum_b200 import _lib
     from ouzelum_b200.sim import QuadSim
-    from ouzelum_b200.dist import allreduce_metrics, rank_info
+    from ouzelum_b200.dist import allreduce_metrics, bind_to_gpu_numa_node, rank_info
 
     rank, world, local = rank_info()
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa_node(local)      # before any pinned allocation: host buffers land on the GPU's own NUMA node
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
@@ -445,23 +447,37 @@ def run_ours(args):
             # (zero-copy over PCIe); step_host() returns after a stream synchronise, results are valid on the host
             env.step_host(h_act[k & 3])
 
-        def timed(fn):
+        e2e_ranks = {}
+
+        def timed(fn, tag=None):
             for k in range(W):
                 fn(k)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lat = []
             e0.record()
             for k in range(K):
+                t0 = time.perf_counter()
                 fn(k)
+                lat.append(time.perf_counter() - t0)
             e1.record()
             barrier()
             te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if tag is not None:
+                lat.sort()
+                mine = torch.tensor([float(te.item()) / K * 1e3, lat[len(lat) // 2] * 1e6, lat[min(len(lat) - 1, int(0.99 * len(lat)))] * 1e6],
+                                    dtype=torch.float64, device=dev)
+                allr = [mine.clone() for _ in range(world)]
+                if world > 1:
+                    dist.all_gather(allr, mine)
+                e2e_ranks[tag] = [{"rank": r_, "us_per_step_device": float(v[0]), "host_p50_us": float(v[1]), "host_p99_us": float(v[2])}
+                                  for r_, v in enumerate(allr)]
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             return world * n * K / (float(te.item()) * 1e-3)
 
         v_copy = timed(e2e_step)
-        v_host = timed(e2e_step_host)
+        v_host = timed(e2e_step_host, "step_host")
         env.close()
         # EnvPool-style pipelining for a consumer that can work on halves: two task objects of n/2 envs on two streams; while the
         # host consumes half A's results and writes its next actions, half B's step (action reads, compute, PCIe write-back) runs
@@ -491,6 +507,7 @@ def run_ours(args):
                "h2d_bytes_per_step": world * h_act[0].numel() * 4,
                "d2h_bytes_per_step": world * (n * 13 * 4 + n * 4 + n * 8 + n),
                "api": "ouzelum_b200.make(...).step_host(pinned actions) -> pinned (obs f32 [N,13], reward f32 [N], reset int64 [N]; + the same flags as u8): one launch, zero-copy PCIe reads/writes inside the kernel, stream sync",
+               "per_rank": e2e_ranks.get("step_host"), "numa_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)} cpus)" if numa_cpus else None),
                "value_pipelined_two_halves": v_halves,
                "pipelined_two_halves": "two task objects of n/2 envs on two streams, step_host_async / step_host_wait: one half's PCIe write-back overlaps the other half's step (for consumers that can work on halves; not the reference's synchronous step)",
                "value_with_explicit_copies": v_copy,
@@ -579,6 +596,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)         # the CPU arm gets every host core again (the GPU arm was bound to one NUMA node)
         v, steps_c, envs_c, threads = cpu_port_rate(n, budget_s=8.0, seed=args.seed, flavour="c")
         vt, steps_t, envs_t, _ = cpu_port_rate(n, budget_s=6.0, seed=args.seed, flavour="torch")
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -15,6 +15,38 @@ def rank_info():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin the calling process to the CPUs (and therefore, by first touch, the memory) of the NUMA node the GPU hangs off.
+
+    A host consumer exchanges ~1.3 MB per 16384-env step with its GPU through pinned buffers (zero-copy PCIe reads / writes);
+    torchrun does not bind its workers, so on a two-socket box half of the ranks would otherwise reach their GPU across the
+    inter-socket link.  Returns the CPU list it bound to (None if the topology could not be read -- nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                       # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed) or None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 -- best effort: containers may hide sysfs / NVML
+        return None
+
+
 def shard(total_envs: int, rank: int, world: int):
     """Contiguous block owned by `rank`: returns (num_local_envs, env_id_base).  The first `total % world` ranks get one
     extra env, so any total is covered exactly once."""

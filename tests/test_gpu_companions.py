@@ -108,8 +108,8 @@ def test_pv_filter_float32_error_vs_float64_arbiter():
         sc, scc = np.abs(s64).max() + 1.0, np.abs(c64).max()
         e_ref_s, e_gpu_s = np.abs(sref - s64).max() / sc, np.abs(x - s64).max() / sc
         e_ref_c, e_gpu_c = np.abs(cref - c64).max() / scc, np.abs(P - c64).max() / scc
-        assert e_gpu_s <= 4.0 * e_ref_s + 2e-7, (t, e_gpu_s, e_ref_s)
-        assert e_gpu_c <= 4.0 * e_ref_c + 2e-7, (t, e_gpu_c, e_ref_c)
+        assert e_gpu_s <= 4.0 * e_ref_s + 1e-6, (t, e_gpu_s, e_ref_s)       # floor: 8 float32 ulp of the scale
+        assert e_gpu_c <= 4.0 * e_ref_c + 1e-6, (t, e_gpu_c, e_ref_c)
         ratios.append((e_gpu_s / max(e_ref_s, 1e-12), e_gpu_c / max(e_ref_c, 1e-12)))
         nofix = ~(d["pos_fix"][t] | d["vel_fix"][t])
         np.testing.assert_allclose(x[nofix], sref[nofix], rtol=1e-5, atol=1e-5 * sc, err_msg=f"predict-only state t={t}")

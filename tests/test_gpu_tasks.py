@@ -497,19 +497,23 @@ def test_graphed_rollout_collection_runs_and_tracks_step_counter(tmp_path):
 
 def test_graphed_rollout_equals_eager_collection_bit_for_bit():
     """(f)1: `GraphedRollout.run()` (one CUDA graph per 16-step rollout) against the eager `collect_rollout` loop of
-    RPO-LSTM/main.py:89-112 under fixed seeds: every stored tensor must agree bit for bit.  The policy is made deterministic
-    (log-std -40: the sampled action equals the mean in float32) so that the comparison does not depend on how the CUDA
-    generator's offsets advance inside / outside graph capture; env, vehicle and sensor-fault randomness is counter-based."""
+    RPO-LSTM/main.py:89-112 under fixed seeds: every stored tensor must agree bit for bit.  The policy acts with its MEAN (a
+    subclass that skips the sampling) so that the comparison does not depend on how the CUDA generator's offsets advance inside /
+    outside graph capture; env, vehicle and sensor-fault randomness is counter-based."""
     import ouzelum_b200
     from ouzelum_b200.pomdp import POMDPWrapper
     from ouzelum_b200.rollout import GraphedRollout, RecurrentActor, RolloutStorage, collect_rollout, initial_rollout_state
     n, T = 1024, 16
     mk = lambda: ouzelum_b200.make(seed=8, task="Landing", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
                                    cfg=ouzelum_b200.task_config("Landing", n, seed=8, maxEpisodeLength=50, rotorFault={"enable": True}))
+    class MeanActor(RecurrentActor):
+        def forward(self, obs, lstm_state, done, action=None):
+            mean, std, lstm_state = self.distribution(obs, lstm_state, done)
+            logp, ent = self.log_prob_entropy(mean, std, mean)
+            return mean, logp, ent, lstm_state
     torch.manual_seed(0)
-    actor = RecurrentActor().to(DEV)
+    actor = MeanActor().to(DEV)
     with torch.no_grad():
-        actor.actor_logstd.fill_(-40.0)
         actor.actor_mean.weight.mul_(30.0)                      # actions large enough to move the vehicle (init gain is 0.01)
     e_eager, e_graph = mk(), mk()
     s_eager, s_graph = RolloutStorage(T, n, 13, 4, DEV), RolloutStorage(T, n, 13, 4, DEV)

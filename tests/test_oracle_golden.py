@@ -139,8 +139,8 @@ def test_pv_filter_float32_error_is_inherent_float64_arbiter():
         sc, scc = np.abs(s64).max() + 1.0, np.abs(c64).max()
         e_ref_s, e_ora_s = np.abs(sref - s64).max() / sc, np.abs(s32 - s64).max() / sc
         e_ref_c, e_ora_c = np.abs(cref - c64).max() / scc, np.abs(c32 - c64).max() / scc
-        assert e_ora_s <= 4.0 * e_ref_s + 2e-7, (t, e_ora_s, e_ref_s)
-        assert e_ora_c <= 4.0 * e_ref_c + 2e-7, (t, e_ora_c, e_ref_c)
+        assert e_ora_s <= 4.0 * e_ref_s + 1e-6, (t, e_ora_s, e_ref_s)       # floor: 8 float32 ulp of the scale
+        assert e_ora_c <= 4.0 * e_ref_c + 1e-6, (t, e_ora_c, e_ref_c)
         worst = max(worst, e_ref_s, e_ref_c)
         nofix = ~(d["pos_fix"][t] | d["vel_fix"][t])
         assert nofix.any()
