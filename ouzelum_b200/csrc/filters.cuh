@@ -29,6 +29,13 @@ __device__ __forceinline__ void pv_quat_to_R(float r, float i, float j, float k,
     R[2][0] = two_s * fmaf(i, k, -(j * r)); R[2][1] = two_s * fmaf(j, k, i * r); R[2][2] = fmaf(-two_s, fmaf(j, j, i * i), 1.f);
 }
 
+#ifndef OZL_PV_UNROLL
+#define OZL_PV_UNROLL 1     // unroll factor of the rolled 9-iteration covariance loops (A/B knob; 1 or 3)
+#endif
+#define OZL_PRAGMA_(x) _Pragma(#x)
+#define OZL_PRAGMA(x) OZL_PRAGMA_(x)
+#define OZL_PV_LOOP OZL_PRAGMA(unroll OZL_PV_UNROLL)
+
 template <int STRIDE>
 struct PVShared {
     float x[9];
@@ -67,7 +74,7 @@ __device__ __forceinline__ void pv_predict(PVShared<STRIDE>& s, const float acc[
         }
     }
     // ---- M = F P, one column per iteration
-#pragma unroll 1
+    OZL_PV_LOOP
     for (int c = 0; c < 9; ++c) {
         float pp[3], pv[3], pb[3];
 #pragma unroll
@@ -80,7 +87,7 @@ __device__ __forceinline__ void pv_predict(PVShared<STRIDE>& s, const float acc[
         }
     }
     // ---- N = M F^T, one row per iteration
-#pragma unroll 1
+    OZL_PV_LOOP
     for (int r = 0; r < 9; ++r) {
         float mp[3], mv[3], mb[3];
 #pragma unroll
@@ -142,7 +149,7 @@ __device__ __forceinline__ void pv_correct(PVShared<STRIDE>& s, const float z[3]
     float xn[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) xn[i] = s.x[i];
-#pragma unroll 1
+    OZL_PV_LOOP
     for (int i = 0; i < 9; ++i) {
         float row[9];
 #pragma unroll
@@ -181,53 +188,43 @@ __device__ __forceinline__ void ekf_update(EKF4& s, const double g[3], const dou
     double nq = sqrt(fma(s.q[3], s.q[3], fma(s.q[2], s.q[2], fma(s.q[1], s.q[1], s.q[0] * s.q[0]))));
     double q[4] = {s.q[0] / nq, s.q[1] / nq, s.q[2] / nq, s.q[3] / nq};
     const double hd = 0.5 * Dt;
-    // Omega(x) rows: [0,-x0,-x1,-x2],[x0,0,x2,-x1],[x1,-x2,0,x0],[x2,x1,-x0,0]          (:1100-1106)
-    double Om[4][4] = {{0.0, -g[0], -g[1], -g[2]}, {g[0], 0.0, g[2], -g[1]}, {g[1], -g[2], 0.0, g[0]}, {g[2], g[1], -g[0], 0.0}};
-    double qt[4], F[4][4];
+    // Omega(x) rows: [0,-x0,-x1,-x2],[x0,0,x2,-x1],[x1,-x2,0,x0],[x2,x1,-x0,0]          (:1100-1106); zero diagonal, so the
+    // products with I + c Omega are written as "identity term + the three off-diagonal terms" (48 instead of 64 multiply-adds)
+    const double x[3] = {hd * g[0], hd * g[1], hd * g[2]};                // F = I + Omega(0.5 Dt g)      (:1157-1158)
+    const double Ox[4][4] = {{0.0, -x[0], -x[1], -x[2]}, {x[0], 0.0, x[2], -x[1]}, {x[1], -x[2], 0.0, x[0]}, {x[2], x[1], -x[0], 0.0}};
+    double qt[4];                                                         // q_t = (I + 0.5 Dt Omega(g)) q    (:1132-1133)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        double acc = 0.0;
+        double acc = q[i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double a = (i == j ? 1.0 : 0.0) + hd * Om[i][j];       // (I + 0.5 Dt Omega) q        (:1132-1133)
-            acc = fma(a, q[j], acc);
-        }
+        for (int j = 0; j < 4; ++j)
+            if (j != i) acc = fma(Ox[i][j], q[j], acc);
         qt[i] = acc;
     }
-    const double x[3] = {hd * g[0], hd * g[1], hd * g[2]};                // F = I + Omega(0.5 Dt g)      (:1157-1158)
-    double Ox[4][4] = {{0.0, -x[0], -x[1], -x[2]}, {x[0], 0.0, x[2], -x[1]}, {x[1], -x[2], 0.0, x[0]}, {x[2], x[1], -x[0], 0.0}};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) F[i][j] = (i == j ? 1.0 : 0.0) + Ox[i][j];
-    // W = 0.5 Dt [ -q_v ; q_w I + skew(q_v) ]                                                         (:1320)
-    double W[4][3] = {{-q[1], -q[2], -q[3]}, {q[0], -q[3], q[2]}, {q[3], q[0], -q[1]}, {-q[2], q[1], q[0]}};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) W[i][j] = hd * W[i][j];
-    // P_t = F P F^T + 0.5 Dt g_noise W W^T                                                            (:1321-1322)
+    // P_t = F P F^T + 0.5 Dt g_noise W W^T with W = 0.5 Dt [ -q_v ; q_w I + skew(q_v) ]                (:1320-1322);
+    // W W^T = (0.5 Dt)^2 (|q|^2 I - q q^T) for this 4x3 quaternion-rate matrix
     double FP[4][4], Pt[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double a = 0.0;
+            double a = s.P[i][j];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a = fma(F[i][k], s.P[k][j], a);
+            for (int k = 0; k < 4; ++k)
+                if (k != i) a = fma(Ox[i][k], s.P[k][j], a);
             FP[i][j] = a;
         }
-    const double qs = hd * g_noise;
+    const double n2 = fma(q[3], q[3], fma(q[2], q[2], fma(q[1], q[1], q[0] * q[0])));
+    const double qw = (hd * g_noise) * (hd * hd);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double a = 0.0, ww = 0.0;
+            double a = FP[i][j];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a = fma(FP[i][k], F[j][k], a);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ww = fma(W[i][k], W[j][k], ww);
-            Pt[i][j] = fma(qs, ww, a);
+            for (int k = 0; k < 4; ++k)
+                if (k != j) a = fma(FP[i][k], Ox[j][k], a);
+            Pt[i][j] = fma(qw, (i == j ? n2 : 0.0) - q[i] * q[j], a);
         }
     // S = P_t + eps I ; K = P_t S^-1  (Gauss-Jordan on the SPD 4x4, no pivoting)                       (:1332-1333)
     double S[4][4], Si[4][4];
@@ -248,17 +245,10 @@ __device__ __forceinline__ void ekf_update(EKF4& s, const double g[3], const dou
             for (int j = 0; j < 4; ++j) { S[r][j] = fma(-f, S[c][j], S[r][j]); Si[r][j] = fma(-f, Si[c][j], Si[r][j]); }
         }
     }
-    double K[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a = fma(Pt[i][k], Si[k][j], a);
-            K[i][j] = a;
-        }
-    // P = (I - K) P_t ; q = normalize(q_t + K (ang - q_t))                                             (:1334-1336)
+    // With H = I (the `ang` branch) the update collapses: K = P_t S^-1 = (S - eps I) S^-1 = I - eps S^-1, hence
+    //   q = q_t + K (ang - q_t) = ang - eps S^-1 (ang - q_t)          P = (I - K) P_t = eps S^-1 P_t = eps K = eps (I - eps S^-1)
+    // (:1334-1336) -- 36 multiply-adds instead of the three 4x4 products (144); agrees with the literal evaluation to ~1e-15
+    // relative (the CPU oracle evaluates the reference's formulas literally; parity bound 1e-9).
     double v[4], qn[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = ang[i] - qt[i];
@@ -266,15 +256,10 @@ __device__ __forceinline__ void ekf_update(EKF4& s, const double g[3], const dou
     for (int i = 0; i < 4; ++i) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a = fma(K[i][k], v[k], a);
-        qn[i] = qt[i] + a;
+        for (int k = 0; k < 4; ++k) a = fma(Si[i][k], v[k], a);
+        qn[i] = fma(-s_eps, a, ang[i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double b = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) b = fma((i == k ? 1.0 : 0.0) - K[i][k], Pt[k][j], b);
-            s.P[i][j] = b;
-        }
+        for (int j = 0; j < 4; ++j) s.P[i][j] = s_eps * ((i == j ? 1.0 : 0.0) - s_eps * Si[i][j]);
     }
     const double nn = sqrt(fma(qn[3], qn[3], fma(qn[2], qn[2], fma(qn[1], qn[1], qn[0] * qn[0]))));
 #pragma unroll
