@@ -86,20 +86,22 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     // ---- stage-0 loads (registers) and L2 prefetches of everything the later stages will read
     bool rst = false;
     float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
-    float wz0 = 0.f, pvl[3] = {0.f, 0.f, 0.f};
+    float wz0 = 0.f, pvl[3] = {0.f, 0.f, 0.f}, wp[3] = {0.f, 0.f, 0.f};
+    float4 hpose = d0;
+    int2 hidx = make_int2(0, 0);
     if (valid) {
         rst = a.reset[i] != 0;
+        if (WITH_STEP) { hpose = h.pose[i]; hidx = h.idx[i]; }
         d0 = *plane4_ptr(pl, 0, i); d1 = *plane4_ptr(pl, 1, i); d2 = *plane4_ptr(pl, 2, i);
         wz0 = plane4_ptr(pl, 3, i)->x;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) pvl[j] = a.prev_linvel[i * 3 + j];
+        for (int j = 0; j < 3; ++j) { pvl[j] = a.prev_linvel[i * 3 + j]; wp[j] = a.waypoint[i * 3 + j]; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) prefetch_l2(a.ekf_q + (int64_t)k * a.n + i);
 #pragma unroll
         for (int k = 0; k < 16; ++k) prefetch_l2(a.ekf_P + (int64_t)k * a.n + i);
 #pragma unroll
         for (int k = 0; k < 9; ++k) prefetch_l2(a.pv_x + (int64_t)k * a.n + i);
-        prefetch_l2(a.waypoint + i * 3);
         if (WITH_STEP) {
             prefetch_l2(plane2_ptr(pl, i));
 #pragma unroll
@@ -123,7 +125,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     float q[4], w[3], est_p[3], est_v[3], cmd[4];
     float tgt[3] = {0.f, 0.f, 0.f};
     if (valid) {
-        if (WITH_STEP) husky_step_env(h, i, step, tgt);     // landing target for this step (landing.py:373-374)
+        if (WITH_STEP) husky_step_env(h, i, step, tgt, hpose, hidx);     // landing target for this step (landing.py:373-374)
         // ---- true root state (post reset_idx)
         float p[3], v[3];
         if (rst) {
@@ -196,7 +198,6 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         float t[3];
         if (WITH_STEP) { t[0] = tgt[0]; t[1] = tgt[1]; t[2] = tgt[2]; }
         else { t[0] = a.target[i * 3]; t[1] = a.target[i * 3 + 1]; t[2] = a.target[i * 3 + 2]; }
-        float wp[3] = {a.waypoint[i * 3], a.waypoint[i * 3 + 1], a.waypoint[i * 3 + 2]};
         waypoint_update(p, t, wp, warm);
         for (int j = 0; j < 3; ++j) a.waypoint[i * 3 + j] = wp[j];
         if (a.est13) {

@@ -130,20 +130,24 @@ __device__ __forceinline__ void pv_correct(PVShared<STRIDE>& s, const float z[3]
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) S[i][j] = PH[i][LO + j] + (i == j ? rvar[i] : 0.f);
-    // 3x3 inverse by the adjugate
-    const float c00 = fmaf(S[1][1], S[2][2], -(S[1][2] * S[2][1]));
-    const float c01 = fmaf(S[1][2], S[2][0], -(S[1][0] * S[2][2]));
-    const float c02 = fmaf(S[1][0], S[2][1], -(S[1][1] * S[2][0]));
-    const float det = fmaf(S[0][2], c02, fmaf(S[0][1], c01, S[0][0] * c00));
-    const float id = 1.0f / det;
+    // 3x3 inverse by the adjugate, evaluated in float64 and rounded to float32 once.  After the first fix P[H,H] is of the order
+    // of R = 1e-7 with strongly correlated entries; the float32 adjugate loses most of its digits to cancellation there (the
+    // reference's torch.linalg.inv is a pivoted LU), and the innovation gain inherits the error (measured against a float64
+    // evaluation of the whole step: 1.7e-4 of the state scale with the float32 adjugate, 1e-7 for the reference).
     float Si[3][3];
-    Si[0][0] = c00 * id; Si[1][0] = c01 * id; Si[2][0] = c02 * id;
-    Si[0][1] = fmaf(S[0][2], S[2][1], -(S[0][1] * S[2][2])) * id;
-    Si[1][1] = fmaf(S[0][0], S[2][2], -(S[0][2] * S[2][0])) * id;
-    Si[2][1] = fmaf(S[0][1], S[2][0], -(S[0][0] * S[2][1])) * id;
-    Si[0][2] = fmaf(S[0][1], S[1][2], -(S[0][2] * S[1][1])) * id;
-    Si[1][2] = fmaf(S[0][2], S[1][0], -(S[0][0] * S[1][2])) * id;
-    Si[2][2] = fmaf(S[0][0], S[1][1], -(S[0][1] * S[1][0])) * id;
+    {
+        const double s00 = S[0][0], s01 = S[0][1], s02 = S[0][2], s10 = S[1][0], s11 = S[1][1], s12 = S[1][2];
+        const double s20 = S[2][0], s21 = S[2][1], s22 = S[2][2];
+        const double c00 = fma(s11, s22, -(s12 * s21)), c01 = fma(s12, s20, -(s10 * s22)), c02 = fma(s10, s21, -(s11 * s20));
+        const double id = 1.0 / fma(s02, c02, fma(s01, c01, s00 * c00));
+        Si[0][0] = (float)(c00 * id); Si[1][0] = (float)(c01 * id); Si[2][0] = (float)(c02 * id);
+        Si[0][1] = (float)(fma(s02, s21, -(s01 * s22)) * id);
+        Si[1][1] = (float)(fma(s00, s22, -(s02 * s20)) * id);
+        Si[2][1] = (float)(fma(s01, s20, -(s00 * s21)) * id);
+        Si[0][2] = (float)(fma(s01, s12, -(s02 * s11)) * id);
+        Si[1][2] = (float)(fma(s02, s10, -(s00 * s12)) * id);
+        Si[2][2] = (float)(fma(s00, s11, -(s01 * s10)) * id);
+    }
     const float inn[3] = {z[0] - s.x[LO], z[1] - s.x[LO + 1], z[2] - s.x[LO + 2]};
     // one row of K, x and P per iteration: row i of K needs only row i of the old P, read before the row is overwritten
     float xn[9];

@@ -44,10 +44,9 @@ __device__ __forceinline__ void redraw(const HuskyArgs& a, uint32_t genv, uint64
 
 // One control step of the vehicle of env i; writes pose / waypoint index / wheel speeds / the landing target riding on the
 // vehicle, and returns that target in `tgt_out` (for kernels that go on to use it from registers).
-__device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, uint64_t step, float tgt_out[3]) {
+// (`p`, `id`: the vehicle's pose / trajectory record, loaded by the caller -- early, so that the DRAM round trip is off the path)
+__device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, uint64_t step, float tgt_out[3], float4 p, int2 id) {
     const uint32_t genv = a.env_id_base + (uint32_t)i;
-    float4 p = a.pose[i];
-    int2 id = a.idx[i];
     // re-spawn a strayed vehicle when its drone resets (landing.py:263-270)
     if (a.reset && a.reset[i] != 0 && (fabsf(p.x) > a.respawn_limit || fabsf(p.y) > a.respawn_limit)) {
         const uint4 r = draw(a.seed, genv, step, P_HUSKY + 1);
@@ -91,6 +90,10 @@ __device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, ui
     a.target3[i * 3 + 1] = p.y;
     a.target3[i * 3 + 2] = a.target_z;
     tgt_out[0] = p.x + a.x_offset; tgt_out[1] = p.y; tgt_out[2] = a.target_z;
+}
+
+__device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, uint64_t step, float tgt_out[3]) {
+    husky_step_env(a, i, step, tgt_out, a.pose[i], a.idx[i]);
 }
 
 }  // namespace ozl
