@@ -6,9 +6,8 @@
 //   * the step index, warm-up flag and the shared sensor-trigger counters come from the env's DEVICE step counter, so the
 //     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
 //   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
-#ifndef OZL_FUSED_PHILOX_INLINE
-#define OZL_PHILOX_NOINLINE 1
-#endif
+// (OZL_PHILOX_NOINLINE would keep ONE out-of-line copy of the counter RNG for the ~22 draw sites of this kernel: 20 KB less code,
+//  but measured slower on B200 -- 28.2 vs 27.1 us per 65536-env step -- so the draws stay inline)
 #include <cstdlib>
 #include "internal.h"
 #include "bulk_copy.cuh"
@@ -56,8 +55,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 //   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared)
 //   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
 //   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
-//   * the counter RNG is called out of line in this TU (OZL_PHILOX_NOINLINE): ~22 draw sites would otherwise add ~25 KB of
-//     straight-line code to a kernel that already exceeds the instruction caches (round 1: 23 % of stalls were `no_instruction`)
 // WITH_STEP = true is the WHOLE EKFLeeLanded control step in one launch (ozl_ekf_lee_landed_step): the ground vehicle that
 // carries the target runs first (targets.cuh), and after the controller the same thread applies its wrench to its env --
 // env_step(ACT_WRENCH) with the vehicle's target, sensor-fault epilogue on the observation, stores, episode statistics and

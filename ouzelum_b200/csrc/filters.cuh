@@ -30,7 +30,7 @@ __device__ __forceinline__ void pv_quat_to_R(float r, float i, float j, float k,
 }
 
 #ifndef OZL_PV_UNROLL
-#define OZL_PV_UNROLL 1     // unroll factor of the rolled 9-iteration covariance loops (A/B knob; 1 or 3)
+#define OZL_PV_UNROLL 3     // unroll factor of the 9-iteration covariance loops (measured on B200, config 3: 1 -> 3: 27.1 -> 26.8 us)
 #endif
 #define OZL_PRAGMA_(x) _Pragma(#x)
 #define OZL_PRAGMA(x) OZL_PRAGMA_(x)
@@ -189,8 +189,9 @@ struct EKF4 {
 __device__ __forceinline__ void ekf_update(EKF4& s, const double g[3], const double ang[4], double Dt, double g_noise,
                                            double s_eps) {
     // caller-side normalisation (tasks/ekf_lee_landed.py:386: q=self.Q_state[idx]/np.linalg.norm(...))
-    double nq = sqrt(fma(s.q[3], s.q[3], fma(s.q[2], s.q[2], fma(s.q[1], s.q[1], s.q[0] * s.q[0]))));
-    double q[4] = {s.q[0] / nq, s.q[1] / nq, s.q[2] / nq, s.q[3] / nq};
+    // (one reciprocal + four products instead of four float64 divisions: 1 ulp of float64 apart, parity bound 1e-9)
+    const double inq = 1.0 / sqrt(fma(s.q[3], s.q[3], fma(s.q[2], s.q[2], fma(s.q[1], s.q[1], s.q[0] * s.q[0]))));
+    double q[4] = {s.q[0] * inq, s.q[1] * inq, s.q[2] * inq, s.q[3] * inq};
     const double hd = 0.5 * Dt;
     // Omega(x) rows: [0,-x0,-x1,-x2],[x0,0,x2,-x1],[x1,-x2,0,x0],[x2,x1,-x0,0]          (:1100-1106); zero diagonal, so the
     // products with I + c Omega are written as "identity term + the three off-diagonal terms" (48 instead of 64 multiply-adds)
@@ -249,25 +250,38 @@ __device__ __forceinline__ void ekf_update(EKF4& s, const double g[3], const dou
             for (int j = 0; j < 4; ++j) { S[r][j] = fma(-f, S[c][j], S[r][j]); Si[r][j] = fma(-f, Si[c][j], Si[r][j]); }
         }
     }
-    // With H = I (the `ang` branch) the update collapses: K = P_t S^-1 = (S - eps I) S^-1 = I - eps S^-1, hence
-    //   q = q_t + K (ang - q_t) = ang - eps S^-1 (ang - q_t)          P = (I - K) P_t = eps S^-1 P_t = eps K = eps (I - eps S^-1)
-    // (:1334-1336) -- 36 multiply-adds instead of the three 4x4 products (144); agrees with the literal evaluation to ~1e-15
-    // relative (the CPU oracle evaluates the reference's formulas literally; parity bound 1e-9).
+    // K = P_t S^-1 ; P = (I - K) P_t ; q = normalize(q_t + K (ang - q_t)), evaluated as the reference writes them (:1333-1336).
+    // (With H = I the update collapses algebraically to q = ang - eps S^-1 (ang - q_t), P = eps (I - eps S^-1), a third of the
+    // work -- but `I - K` cancels to ~1e-9 relative in the literal form when P_t >> eps, so the two forms differ by up to 1e-9 in
+    // later steps; parity with the reference's arithmetic is worth more here than ~100 float64 instructions.)
     double v[4], qn[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = ang[i] - qt[i];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i) {               // one row of K at a time (row i of K feeds only q[i] and row i of P)
+        double Ki[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a = fma(Pt[i][k], Si[k][j], a);
+            Ki[j] = a;
+        }
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a = fma(Si[i][k], v[k], a);
-        qn[i] = fma(-s_eps, a, ang[i]);
+        for (int k = 0; k < 4; ++k) a = fma(Ki[k], v[k], a);
+        qn[i] = qt[i] + a;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s.P[i][j] = s_eps * ((i == j ? 1.0 : 0.0) - s_eps * Si[i][j]);
+        for (int j = 0; j < 4; ++j) {
+            double b = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b = fma((i == k ? 1.0 : 0.0) - Ki[k], Pt[k][j], b);
+            s.P[i][j] = b;
+        }
     }
-    const double nn = sqrt(fma(qn[3], qn[3], fma(qn[2], qn[2], fma(qn[1], qn[1], qn[0] * qn[0]))));
+    const double inn = 1.0 / sqrt(fma(qn[3], qn[3], fma(qn[2], qn[2], fma(qn[1], qn[1], qn[0] * qn[0]))));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s.q[i] = qn[i] / nn;
+    for (int i = 0; i < 4; ++i) s.q[i] = qn[i] * inn;
 }
 
 }  // namespace ozl

@@ -57,7 +57,7 @@ def test_one_launch_ekf_lee_landed_step_vs_oracle(n, steps):
         wrench_o, est_o, cmd_o = glue.pre_physics(root, tgt, reset_before)
         # ---- estimator / controller (E1-E3, V1-V2, L, L')
         np.testing.assert_allclose(env.ekf.Q_state.cpu().numpy(), glue.Q, rtol=1e-9, atol=1e-12, err_msg=f"EKF q t={t}")
-        np.testing.assert_allclose(env.ekf.P.cpu().numpy(), glue.ekf.P, rtol=1e-6, atol=1e-7 * np.abs(glue.ekf.P).max(), err_msg=f"EKF P t={t}")
+        np.testing.assert_allclose(env.ekf.P.cpu().numpy(), glue.ekf.P, rtol=1e-7, atol=1e-9 * np.abs(glue.ekf.P).max(), err_msg=f"EKF P t={t}")
         assert np.array_equal(env.prev_root_linvels.cpu().numpy(), root[:, 7:10])
         x, P = env.pvfilters.get_states().cpu().numpy(), env.pvfilters.get_covariances().cpu().numpy()
         sx, sP = np.abs(glue.pv.state).max() + 1.0, np.abs(glue.pv.cov).max() + 1.0
