@@ -161,6 +161,10 @@ int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream);
  * a bare cudaStreamSynchronize (so that a binding needs no CUDA runtime of its own). */
 int ozl_step_host_launch(ozl_env* env, const ozl_host_io* io, void* stream);
 int ozl_stream_sync(void* stream);
+/* Completion of the last ozl_step_host* launch of `env`: polls the completion word the step kernel's last block writes to pinned
+ * host memory after all its result stores (a stream synchronise costs ~6 us more per step); falls back to synchronising
+ * `stream` if the word does not arrive (which also reports CUDA errors).  ozl_step_host_sync = launch + this. */
+int ozl_step_host_wait(ozl_env* env, void* stream);
 
 /* Same step with the target supplied by the caller every step instead of being re-sampled in-kernel: the landing
  * family, whose target rides on a ground vehicle (tasks/landing.py:373-374, lando.py, landed.py).  target3 [N,3] f32. */

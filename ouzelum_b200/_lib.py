@@ -154,6 +154,7 @@ _SIGS = {
     "ozl_step_host_sync": (C.c_int, [_P, _P, _P]),
     "ozl_step_host_launch": (C.c_int, [_P, _P, _P]),
     "ozl_stream_sync": (C.c_int, [_P]),
+    "ozl_step_host_wait": (C.c_int, [_P, _P]),
     "ozl_step_tracking": (C.c_int, [_P] * 10),
     "ozl_step_wrench": (C.c_int, [_P] * 10),
     "ozl_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

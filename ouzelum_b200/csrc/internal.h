@@ -67,6 +67,11 @@ struct ozl_env {
     int use_pdl;                // step launches carry the programmatic-stream-serialization attribute (see launch_step)
     void* arena;                // single cudaMalloc backing all planes
     size_t arena_bytes;
+    // host-consumer steps: completion word in pinned host memory, written by the last block of a step kernel after all its
+    // zero-copy result stores (ozl_step_host_sync / ozl_step_host_wait poll it instead of synchronising the stream)
+    volatile unsigned int* host_done;   // cudaHostAlloc'ed, one word
+    unsigned int host_seq;              // sequence number of the last host step launched
+    int use_host_flag;                  // OZL_HOST_FLAG=0 turns the completion word off (stream synchronise instead)
 };
 
 // Step launches go through cudaLaunchKernelEx so that they can carry the programmatic-stream-serialization attribute (PDL):

@@ -57,7 +57,7 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
                  float* __restrict__ rew, int64_t* __restrict__ reset, int64_t* __restrict__ progress,
                  uint8_t* __restrict__ timeout, float* __restrict__ ep_ret_out, const float* __restrict__ target_in,
                  const int act_mode, uint8_t* __restrict__ done_u8, int64_t* __restrict__ reset_mirror, const int obs_bulk,
-                 const int64_t env0, const FrontArgs fa) {
+                 const int64_t env0, const FrontArgs fa, volatile unsigned int* host_done, const unsigned int host_seq) {
     __shared__ __align__(16) float s_obs[BLOCK * 13];
     __shared__ uint64_t s_step;
 
@@ -162,6 +162,22 @@ quad_step_kernel(const DevCfg c, const Planes pl, const float4* __restrict__ act
 #if OZL_OBS_BULK
     if (threadIdx.x == 0) bulk_wait_read_all();   // s_obs must stay alive until the bulk copy has read it
 #endif
+    // Host consumer: completion word.  Every block orders its zero-copy result stores before a ticket (the barrier makes the
+    // block's stores visible to thread 0, the system-scope fence orders them before the ticket); the block that draws the last
+    // ticket writes the step's sequence number to pinned host memory, where the host is polling -- no stream synchronise, whose
+    // driver path costs ~6 us per step.  (Only in host mode: the device-buffer steps keep their election-free epilogue.)
+    if (host_done) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned long long t = atomicAdd(pl.ctrl + 6, 1ull);
+            if (t == (unsigned long long)gridDim.x - 1ull) {
+                pl.ctrl[6] = 0ull;
+                __threadfence_system();
+                *host_done = host_seq;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K1, TMA-pipelined
@@ -511,7 +527,7 @@ __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         pl.ctrl[0] = step_word0_dev(0ull, c.step_shift); pl.ctrl[1] = 0ull;
-        pl.ctrl[4] = 0ull; pl.ctrl[5] = 0ull;
+        pl.ctrl[4] = 0ull; pl.ctrl[5] = 0ull; pl.ctrl[6] = 0ull;
     }
     if (i < kMetricSlots * kMetricStride) pl.metrics[i] = 0.0;
     if (i >= c.num_envs) return;
@@ -726,6 +742,19 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     p += state;
     e->pl.ctrl = (unsigned long long*)p; p += ctrl;
     e->pl.metrics = (double*)p;
+    {
+        const char* hv = getenv("OZL_HOST_FLAG");
+        e->use_host_flag = hv ? atoi(hv) : 1;
+        e->host_done = nullptr;
+        e->host_seq = 0;
+        void* hp = nullptr;
+        if (e->use_host_flag && cudaHostAlloc(&hp, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            memset(hp, 0, 64);
+            e->host_done = (volatile unsigned int*)hp;
+        } else {
+            cudaGetLastError();        // no pinned word: host steps fall back to cudaStreamSynchronize
+        }
+    }
     *out = e;
     return ozl_reset_all(e, cfg->seed, nullptr);
 }
@@ -734,6 +763,7 @@ extern "C" int ozl_destroy(ozl_env* env) {
     if (!env) return 0;
     cudaSetDevice(env->device);
     cudaFree(env->arena);
+    if (env->host_done) cudaFreeHost((void*)env->host_done);
     delete env;
     return 0;
 }
@@ -759,7 +789,7 @@ static_assert(kStepBlock == kTile, "the step counter retires one work unit per 1
 
 static int launch_step(ozl_env* env, const float* actions, const float* target_in, int act_mode, float* obs, float* rew,
                        int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream, const char* who,
-                       uint8_t* done_u8 = nullptr, int obs_bulk = 1, int64_t* reset_mirror = nullptr) {
+                       uint8_t* done_u8 = nullptr, int obs_bulk = 1, int64_t* reset_mirror = nullptr, int host_flag = 0) {
     if (!env) return set_error("%s: env is NULL", who);
     cudaStream_t st = (cudaStream_t)stream;
     if (!actions || !obs || !rew || !reset || !progress) return set_error("%s: NULL buffer", who);
@@ -779,12 +809,14 @@ static int launch_step(ozl_env* env, const float* actions, const float* target_i
         if (tail)
             quad_step_kernel<kStepBlock, FRONT_NONE><<<1, kStepBlock, 0, st>>>(env->dev, env->pl, (const float4*)actions, obs, rew, reset,
                                                                               progress, timeout, ep_ret, nullptr, ACT_ROTORS, nullptr,
-                                                                              nullptr, 1, full_tiles * kTile, FrontArgs{});
+                                                                              nullptr, 1, full_tiles * kTile, FrontArgs{},
+                                                                              (volatile unsigned int*)nullptr, 0u);
         return check_cuda(cudaGetLastError(), "quad_step_kernel(tail)");
     }
     if (launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_NONE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev, env->pl,
                    (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, target_in, act_mode, done_u8, reset_mirror,
-                   obs_bulk, (int64_t)0, FrontArgs{}))
+                   obs_bulk, (int64_t)0, FrontArgs{}, (volatile unsigned int*)(host_flag ? env->host_done : nullptr),
+                   host_flag ? ++env->host_seq : 0u))
         return check_cuda(cudaGetLastError(), "quad_step_kernel");
     return 0;
 }
@@ -810,11 +842,11 @@ static int launch_front_step(ozl_env* env, int front, const float* actions, cons
     if (front == FRONT_VEHICLE)
         rc = launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_VEHICLE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev,
                         env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, (const float*)nullptr, (int)ACT_ROTORS,
-                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa);
+                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa, (volatile unsigned int*)nullptr, 0u);
     else
         rc = launch_pdl(env, quad_step_kernel<kStepBlock, FRONT_LEE>, dim3(blocks_for(n, kStepBlock)), dim3(kStepBlock), st, env->dev,
                         env->pl, (const float4*)actions, obs, rew, reset, progress, timeout, ep_ret, (const float*)nullptr, (int)ACT_WRENCH,
-                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa);
+                        (uint8_t*)nullptr, (int64_t*)nullptr, 1, (int64_t)0, fa, (volatile unsigned int*)nullptr, 0u);
     if (rc) return check_cuda(cudaGetLastError(), who);
     return 0;
 }
@@ -847,7 +879,22 @@ static int step_host_impl(ozl_env* env, const float* actions_host, float* obs_ho
     if (!done_host) return set_error("ozl_step_host: done_host is NULL");
     // host-mapped (pinned, UVA) buffers: plain coalesced stores over PCIe instead of the TMA bulk store (measured equal)
     return launch_step(env, actions_host, nullptr, ACT_ROTORS, obs_host, rew_host, reset, progress, timeout, ep_ret, stream,
-                       "ozl_step_host", done_host, 0, reset_host);
+                       "ozl_step_host", done_host, 0, reset_host, env && env->use_host_flag && env->host_done);
+}
+
+// Wait for the last host step: poll the completion word (see quad_step_kernel); if it does not flip within ~2 s -- or the word is
+// disabled -- synchronise the stream, which also surfaces any CUDA error.
+static int host_step_wait(ozl_env* env, void* stream) {
+    if (env->use_host_flag && env->host_done) {
+        const unsigned int want = env->host_seq;
+        for (long spins = 0; spins < 400000000L; ++spins) {
+            if (*env->host_done == want) { __atomic_thread_fence(__ATOMIC_ACQUIRE); return 0; }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
 }
 extern "C" int ozl_step_host(ozl_env* env, const float* actions_host, float* obs_host, float* rew_host, uint8_t* done_host,
                              int64_t* reset, int64_t* progress, uint8_t* timeout, float* ep_ret, void* stream) {
@@ -863,7 +910,12 @@ extern "C" int ozl_step_host_launch(ozl_env* env, const ozl_host_io* io, void* s
 extern "C" int ozl_step_host_sync(ozl_env* env, const ozl_host_io* io, void* stream) {
     if (!io) return set_error("ozl_step_host_sync: io is NULL");
     if (ozl_step_host_launch(env, io, stream)) return 1;
-    return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+    return host_step_wait(env, stream);
+}
+
+extern "C" int ozl_step_host_wait(ozl_env* env, void* stream) {
+    if (!env) return set_error("ozl_step_host_wait: env is NULL");
+    return host_step_wait(env, stream);
 }
 
 extern "C" int ozl_stream_sync(void* stream) {

@@ -180,7 +180,7 @@ class X500Task(VecTask):
             _lib.check(1)
 
     def step_host_wait(self):
-        if _lib.lib.ozl_stream_sync(self._host_stream):
+        if _lib.lib.ozl_step_host_wait(self.sim._h, self._host_stream):
             _lib.check(1)
         return self._h_obs, self._h_rew, self._h_reset
 
