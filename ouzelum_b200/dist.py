@@ -42,9 +42,29 @@ def bind_to_gpu_numa_node(gpu_index: int):
         cpus = sorted(cpus & allowed) or None
         if cpus:
             os.sched_setaffinity(0, cpus)
+        _prefer_numa_node(f"/sys/bus/pci/devices/{bus}/numa_node")
         return cpus
     except Exception:  # noqa: BLE001 -- best effort: containers may hide sysfs / NVML
         return None
+
+
+def _prefer_numa_node(numa_node_file):
+    """set_mempolicy(MPOL_PREFERRED, {node}) for the calling thread: pages touched from now on (the pinned I/O buffers) come from the
+    GPU's own NUMA node even when the CPUs this process may run on sit on another one (containers often expose the CPUs of a single
+    socket).  Best effort: a raw syscall, no libnuma needed; silently does nothing when the node is unknown or not allowed."""
+    try:
+        import ctypes
+        with open(numa_node_file) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return False
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        libc = ctypes.CDLL(None, use_errno=True)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238                      # x86_64
+        return libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, 16 * 64) == 0
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def shard(total_envs: int, rank: int, world: int):
