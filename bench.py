@@ -31,7 +31,7 @@ WORKLOAD = "x500 trajectory tracking + single-rotor loss-of-effectiveness fault,
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
 SHARDS = 64                           # independent 16384-env shards the timed steps rotate over (64 x 4.9 MB = 314 MB > 126 MB L2)
 METRICS_EVERY = 16                    # BASELINE config 4: metrics vector read (+ NCCL all-reduce when N > 1) every 16 steps
-METRICS_PHASE = 7                     # ... after steps 7, 23, 39, ...: the asynchronous all-reduce has the following steps to hide behind
+METRICS_PHASE = 4                     # ... after steps 4, 20, 36, ...: the asynchronous all-reduce has the following steps to hide behind (at the driver's K = 20: one read, 15 steps of cover)
 
 
 def config_of(envs_per_gpu, world):

@@ -547,6 +547,11 @@ __global__ void init_state_kernel(const DevCfg c, const Planes pl) {
 
 // 16 warps, one per metric: lanes stride over the slots, then a warp reduction
 __global__ void metrics_read_kernel(const Planes pl, double* out16, int clear) {
+    // PDL: staged behind the step that precedes it on the stream, and the step that follows is staged behind this launch -- a
+    // metrics read every 16 steps no longer breaks the chain of programmatic launches (it cost ~4 us per read: 4.2 -> 4.45 us per
+    // 16384-env step at one read per 16 steps)
+    griddep_wait();
+    griddep_launch_dependents();
     const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
     for (int s = lane; s < kMetricSlots; s += 32) {
@@ -992,6 +997,7 @@ extern "C" int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream) {
 extern "C" int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream) {
     OZL_ENV_CHECK("ozl_metrics_read");
     if (!out16) return set_error("ozl_metrics_read: out16 is NULL");
-    metrics_read_kernel<<<1, 16 * 32, 0, st>>>(env->pl, out16, clear);
-    return check_cuda(cudaGetLastError(), "metrics_read_kernel");
+    if (launch_pdl(env, metrics_read_kernel, dim3(1), dim3(16 * 32), st, env->pl, out16, (int)clear))
+        return check_cuda(cudaGetLastError(), "metrics_read_kernel");
+    return 0;
 }
