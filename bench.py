@@ -43,7 +43,8 @@ def config_of(envs_per_gpu, world):
                   "timed replay, so every timed step starts cold at any K; K steps block-timed with one CUDA-event pair (CUDA graph replay) "
                   "behind a GPU pre-roll that lets the host finish enqueueing before the first event fires",
             "parallelism": f"env-sharded x{world}, no data-path collective; the 16-double metrics vector is read every {METRICS_EVERY} steps "
-                           "INSIDE the timed graph and, for N > 1, all-reduced with NCCL on a side stream inside the same graph"}
+                           "INSIDE the timed graph and, for N > 1, summed over the ranks inside the same graph (NVLink peer-memory "
+                           "exchange issued by the metrics kernel itself; `--metrics-collective nccl`: NCCL all-reduce on a side stream)"}
 
 
 def parse():
@@ -57,6 +58,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-side-configs", action="store_true")
+    p.add_argument("--metrics-collective", default="peer", choices=["peer", "nccl"],
+                   help="N > 1: how the metrics vector is summed over the ranks inside the timed graph")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--roofline-only", action="store_true", help="profiling aid: run only the 1 Mi-env roofline region")
     return p.parse_args()
@@ -290,7 +293,26 @@ def run_ours(args):
     rendezvous = torch.zeros(1, device=dev)
     n_reads = (K + METRICS_EVERY - 1) // METRICS_EVERY + 1
     metrics_ring = torch.zeros(n_reads, 16, dtype=torch.float64, device=dev)
-    nccl_in_graph = world > 1
+    # config 4's only collective, the sum of the 16-double metrics vector over the ranks: NVLink peer-memory exchange issued by the
+    # metrics-read kernel itself (ouzelum_b200/csrc/peer_metrics.cu); `--metrics-collective nccl` keeps the NCCL all-reduce on a
+    # side stream for comparison
+    collective = "none"
+    peer = None
+    if world > 1:
+        collective = args.metrics_collective
+        if collective == "peer":
+            try:
+                from ouzelum_b200.dist import PeerMetrics
+                peer = PeerMetrics(dev)
+            except Exception as e:  # noqa: BLE001 -- no cudaIpc between the ranks on this box: fall back to NCCL, and say so
+                sys.stderr.write(f"[bench] rank {rank}: peer-memory metrics exchange unavailable ({e!r}); using NCCL\n")
+                peer = None
+            flag = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                peer, collective = None, "nccl"
+    nccl_in_graph = collective == "nccl"
+    metrics_sum = torch.zeros(16, dtype=torch.float64, device=dev)
 
     def step_rot(k):
         sm, o_, r_, rs_, pg_, to_, er_ = shards[k % S]
@@ -301,6 +323,10 @@ def run_ours(args):
     def metrics_in_graph(k, with_nccl):
         # one metrics_read kernel on the step stream; the all-reduce forks to the side stream and joins at the end of the capture
         m = metrics_ring[(k // METRICS_EVERY) % n_reads]
+        if peer is not None:
+            # ONE launch: read + 16-byte stores into every rank's mailbox over NVLink; the sum of the previous exchange is folded in
+            peer.push(shards[k % S][0], local=m, prev_sum=metrics_sum)
+            return
         shards[k % S][0].metrics(clear=False, out=m)
         if with_nccl:
             side.wait_stream(torch.cuda.current_stream())
@@ -323,6 +349,8 @@ def run_ours(args):
             if forked[0]:
                 torch.cuda.current_stream().wait_stream(side)     # join the side stream the all-reduces were forked to
                 forked[0] = False
+            if peer is not None and extra is not None:
+                peer.sum(shards[0][0], out=metrics_sum)           # the last exchange of the capture is summed inside it
         return g_
 
     chunk_r = K if K <= 512 else 512
@@ -347,6 +375,7 @@ def run_ours(args):
             nccl_in_graph = False
             gr_rot, gr_rot_rem = build_headline(False)
     n_metric_reads = sum(1 for k in range(K) if (k % METRICS_EVERY) == METRICS_PHASE)
+    n_peer_sums = (reps_r + (1 if rem_r else 0)) if peer is not None else 0
     clocks.region(True)          # NVML sampling (1 ms period) runs from here to the end of the warm-L2 region: the timed replay alone
     gr_rot.replay()              # (K x ~4 us) is shorter than one NVML query, so the window also covers the warm-up replays around it
     if gr_rot_rem is not None:
@@ -375,6 +404,22 @@ def run_ours(args):
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
     rot_ms = float(tr.item())
     value_rot = world * n * K / (rot_ms * 1e-3)
+    peer_check = None
+    if peer is not None:
+        # outside the timed region: the sum the last in-graph exchange produced equals an NCCL all-reduce of the vectors it was fed
+        last_k = max(k for k in range(K) if (k % METRICS_EVERY) == METRICS_PHASE) if n_metric_reads else None
+        if last_k is not None:
+            ref = metrics_ring[(last_k // METRICS_EVERY) % n_reads].clone()
+            gathered = [torch.zeros_like(ref) for _ in range(world)]
+            dist.all_gather(gathered, ref)
+            want = torch.zeros_like(ref)
+            for g_ in gathered:
+                want += g_
+            st_ = peer.status()
+            okf = torch.tensor([1 if (torch.equal(metrics_sum, want) and st_["error"] == 0) else 0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            peer_check = {"sum_equals_rank_ordered_allgather_sum_on_every_rank": bool(okf.item()),
+                          "env_steps_in_summed_vector": float(metrics_sum[8].item()), "exchanges": st_["pushed"]}
     del gr_rot, gr_rot_rem
     shards = shards[:1]
     del b_obs, b_rew, b_epr, b_rst, b_prog, b_tout
@@ -632,11 +677,15 @@ def run_ours(args):
             "config": config_of(n, world),
             "ms_per_rank": per_rank_ms,
             "metrics_reads_in_timed_graph": n_metric_reads, "nccl_allreduce_in_timed_graph": bool(nccl_in_graph),
+            "metrics_collective_in_timed_graph": collective, "peer_exchange": peer_check,
             "value_flush_per_step_events": value_flush, "ms_per_step_flush_per_step_events": ms / K,
             "value_warm_l2": value_warm, "ms_per_step_warm_l2": warm_ms / K,
             "clocks": clocks.result(),
-            "e2e": e2e, "gpu_launches": K + n_metric_reads,
-            "gpu_launches_note": f"{K} quad_step_kernel<128> + {n_metric_reads} metrics_read_kernel per rank inside the timed region"
+            "e2e": e2e, "gpu_launches": K + n_metric_reads + n_peer_sums,
+            "gpu_launches_note": f"{K} quad_step_kernel<128> + {n_metric_reads} "
+                                 + ("metrics_push_kernel (read + NVLink peer stores)" if collective == "peer" else "metrics_read_kernel")
+                                 + (f" + {n_peer_sums} metrics_sum_kernel" if n_peer_sums else "")
+                                 + " per rank inside the timed region"
                                  + (f" (+ {n_metric_reads} NCCL all-reduce kernels, library)" if nccl_in_graph else ""),
             "side_configs": side_configs,
             "roofline": roofline, "roofline_at_workload": roofline_wl,

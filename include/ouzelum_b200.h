@@ -211,6 +211,32 @@ int ozl_set_step_count(ozl_env* env, uint64_t value, void* stream);
  * Replaces RecordEpisodeStatisticsTorch + the trainer's Python scan (RPO-LSTM/utils.py:20-35, main.py:105-113). */
 int ozl_metrics_read(ozl_env* env, double* out16, int32_t clear, void* stream);
 
+/* Multi-GPU sum of the metrics vector over NVLink peer memory (one process per GPU; csrc/peer_metrics.cu).  The only collective
+ * on the path; replaces an NCCL all-reduce of 128 bytes -- and the reference's host-side scan of `infos`
+ * (RPO-LSTM/main.py:105-113) -- with 16-byte self-validating stores into every peer's mailbox, issued by the kernel that reads
+ * the metrics: no collective kernel, no side stream, CUDA-graph capturable (no host-changing argument).
+ *   create            one mailbox per rank (device memory of `device`)
+ *   ipc_handle        64-byte cudaIpcMemHandle_t of the local mailbox, to be all-gathered by the caller (torch.distributed ...)
+ *   connect_ipc       handles of ALL ranks, rank-major (world x 64 bytes); maps the peers' mailboxes
+ *   connect_ptrs      same-process alternative: mailbox pointers (ozl_metrics_xchg_box) and device ordinals of all ranks; enables
+ *                     peer access
+ *   ozl_metrics_push  ozl_metrics_read + store this rank's 16 values into every rank's mailbox; `local16` (optional) receives this
+ *                     rank's own values; if `prev_sum16` is given and an earlier exchange has not been summed yet, its sum is
+ *                     written there first (one launch per exchange in steady state)
+ *   ozl_metrics_sum   sum of the oldest exchange not summed yet, in rank order (bit-identical on every rank) -> sum16; waits for the
+ *                     peers' stores (bounded: 10 s, then NaN and status.error = 1); no-op when nothing is outstanding
+ * A rank may push at most 7 exchanges ahead of the slowest rank's sum. */
+typedef struct ozl_metrics_xchg ozl_metrics_xchg;
+int ozl_metrics_xchg_create(int32_t rank, int32_t world, int32_t device, ozl_metrics_xchg** out);
+int ozl_metrics_xchg_destroy(ozl_metrics_xchg* x);
+int ozl_metrics_xchg_ipc_handle(ozl_metrics_xchg* x, void* handle64);
+int ozl_metrics_xchg_connect_ipc(ozl_metrics_xchg* x, const void* handles64xWorld);
+int ozl_metrics_xchg_box(ozl_metrics_xchg* x, void** out);
+int ozl_metrics_xchg_connect_ptrs(ozl_metrics_xchg* x, void* const* boxes, const int32_t* devices);
+int ozl_metrics_push(ozl_env* env, ozl_metrics_xchg* x, double* local16, double* prev_sum16, int32_t clear, void* stream);
+int ozl_metrics_sum(ozl_env* env, ozl_metrics_xchg* x, double* sum16, void* stream);
+int ozl_metrics_xchg_status(ozl_metrics_xchg* x, uint64_t* pushed, uint64_t* summed, uint64_t* error, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Companion kernels.  All buffers are caller-owned device memory; `n` = number of envs.
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -165,6 +165,15 @@ _SIGS = {
     "ozl_get_step_count": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "ozl_set_step_count": (C.c_int, [_P, C.c_uint64, _P]),
     "ozl_metrics_read": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "ozl_metrics_xchg_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "ozl_metrics_xchg_destroy": (C.c_int, [_P]),
+    "ozl_metrics_xchg_ipc_handle": (C.c_int, [_P, _P]),
+    "ozl_metrics_xchg_connect_ipc": (C.c_int, [_P, _P]),
+    "ozl_metrics_xchg_box": (C.c_int, [_P, C.POINTER(_P)]),
+    "ozl_metrics_xchg_connect_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32)]),
+    "ozl_metrics_push": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
+    "ozl_metrics_sum": (C.c_int, [_P, _P, _P, _P]),
+    "ozl_metrics_xchg_status": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P]),
     "ozl_lee_control": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_float), _P, _P, _P]),
     "ozl_lee_wrench": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_float), C.c_float, _P, _P]),
     "ozl_pv_init": (C.c_int, [C.c_int64, _P, _P, _P]),

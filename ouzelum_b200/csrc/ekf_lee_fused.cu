@@ -16,6 +16,14 @@
 #include "filters.cuh"
 #include "glue.cuh"
 #include "lee_control.cuh"
+#include "tile_chain.cuh"
+
+// Profiling aid (profiles/build_variant.sh ... "-DOZL_ABLATE=<bits>"): drop one stage of the fused step to time the rest.  Results are
+// wrong with any bit set; the product build has OZL_ABLATE == 0 and the branches below fold away.
+#ifndef OZL_ABLATE
+#define OZL_ABLATE 0
+#endif
+#define OZL_KEEP(bit) (!(OZL_ABLATE & (bit)))   // 1 sensor faults, 2 EKF, 4 PV predict, 8 PV fixes, 16 Lee controller, 32 env step
 
 namespace ozl {
 
@@ -39,9 +47,11 @@ struct EkfLeeArgs {
     LeeGains g;
 };
 
-// Envs per CTA: 128 (4 CTAs / SM), 256 (2) or 512 (1).  All give the same 512 resident env-threads per SM at 128 registers; the
-// larger blocks keep more warps in the same phase of this long kernel (see ozl_ekf_lee_block()).
-constexpr int ekf_minb(int block) { return block <= 128 ? 4 : (block <= 256 ? 2 : 1); }
+// Envs per CTA: 64 (8 CTAs / SM), 96 (5), 128 (4), 256 (2) or 512 (1) at 128 registers per thread.  Measured on B200 at config 3
+// (65536 envs, one wave): 96 -> 27.1 us, 128 -> 28.4 us, 64 -> 29.4 us, 256 -> +0.1 us over 128, 512 -> +1.3 us.  65536 envs
+// are 443 envs per SM: with 128-env CTAs the SMs hold 3 or 4 of them (12 or 16 warps) and the launch lasts as long as the SMs
+// with 16; 96-env CTAs spread the same envs as 4 or 5 CTAs (12 or 15 warps).  See ozl_ekf_lee_block().
+constexpr int ekf_minb(int block) { return block <= 64 ? 8 : (block <= 96 ? 5 : (block <= 128 ? 4 : (block <= 256 ? 2 : 1))); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -64,10 +74,16 @@ struct StepIo {
     float* obs; float* rew; int64_t* reset; int64_t* progress; uint8_t* timeout; float* ep_ret;
 };
 
+#ifdef OZL_EKF_MAXNREG
+#define OZL_EKF_BOUNDS(B) __maxnreg__(OZL_EKF_MAXNREG)
+#else
+#define OZL_EKF_BOUNDS(B) __launch_bounds__(B, ekf_minb(B))
+#endif
 template <int kEkfBlock, bool WITH_STEP>
-__global__ void __launch_bounds__(kEkfBlock, ekf_minb(kEkfBlock))
-ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma, const HuskyArgs h, const StepIo io) {
-    static_assert(kEkfBlock >= 96 && kEkfBlock % 32 == 0, "the 81 plane copies of the covariance tile are issued by 81 different threads");
+__global__ void OZL_EKF_BOUNDS(kEkfBlock)
+ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma, const HuskyArgs h, const StepIo io,
+                     const int chain) {
+    static_assert(kEkfBlock % 32 == 0, "whole warps");
     extern __shared__ __align__(128) float s_P[];            // [81][kEkfBlock] covariance tile, later the [kEkfBlock][13] observation tile
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint64_t s_step;
@@ -77,22 +93,38 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     const bool valid = i < a.n;
     const int n_here = (a.n - base) < kEkfBlock ? (int)(a.n - base) : kEkfBlock;
     if (tid == 0 && use_tma) mbar_init(&s_bar, 1);
-    griddep_wait();                    // PDL (bulk_copy.cuh): everything below reads what the previous launch wrote
-    griddep_launch_dependents();
-    if (tid == 0) s_step = read_step(pl.ctrl);
+    // tile-chained launches (tile_chain.cuh): chained == this launch does NOT wait for the previous grid, only for its own tile
+    // chain: -1 classic launch (no tile words touched), 0 first launch of a chain, 1 chained
+    const bool chained = WITH_STEP && chain > 0;
+    const bool chain_words = WITH_STEP && chain >= 0;
+    unsigned long long* const seq = pl.tile_seq + 2 * (size_t)blockIdx.x;
+    if (!chained) {
+        griddep_wait();                // PDL (bulk_copy.cuh): everything below reads what the previous launch wrote
+        if (!chain_words) griddep_launch_dependents();
+        if (tid == 0) {
+            const uint64_t s0 = read_step(pl.ctrl);
+            s_step = s0;
+            if (chain_words) { seq[0] = s0 + 1ull; __threadfence(); }   // visible before this CTA's launch trigger
+        }
+    } else if (tid == 0) {
+        s_step = atomicAdd(seq, 1ull);                                  // returned before this CTA's launch trigger
+    }
     // ---- stage-0 loads (registers) and L2 prefetches of everything the later stages will read
     bool rst = false;
     float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
     float wz0 = 0.f, pvl[3] = {0.f, 0.f, 0.f}, wp[3] = {0.f, 0.f, 0.f};
     float4 hpose = d0;
     int2 hidx = make_int2(0, 0);
-    if (valid) {
+    auto stage0_loads = [&]() {
         rst = a.reset[i] != 0;
         if (WITH_STEP) { hpose = h.pose[i]; hidx = h.idx[i]; }
         d0 = *plane4_ptr(pl, 0, i); d1 = *plane4_ptr(pl, 1, i); d2 = *plane4_ptr(pl, 2, i);
         wz0 = plane4_ptr(pl, 3, i)->x;
 #pragma unroll
         for (int j = 0; j < 3; ++j) { pvl[j] = a.prev_linvel[i * 3 + j]; wp[j] = a.waypoint[i * 3 + j]; }
+    };
+    if (valid) {
+        if (!chained) stage0_loads();  // in flight while the block waits for its leader's read of the step record
 #pragma unroll
         for (int k = 0; k < 4; ++k) prefetch_l2(a.ekf_q + (int64_t)k * a.n + i);
 #pragma unroll
@@ -107,10 +139,17 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         }
     }
     __syncthreads();                   // the mbarrier is initialised, the step index is published
+    if (chain_words) griddep_launch_dependents();   // after the tile's `started` word is final: the next launch's CTAs read it in launch order
+    if (chained) {
+        if (tid == 0) tile_chain_wait(seq, s_step);     // the tile's previous step has been released (acquire)
+        __syncthreads();
+        if (valid) stage0_loads();
+        fence_proxy_async_all();       // the bulk loads below (async proxy) are ordered behind the acquire
+    }
     if (use_tma) {
         const uint32_t bytes = (uint32_t)n_here * 4u;
         if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
-        if (tid < 81) bulk_load_g2s(s_P + tid * kEkfBlock, a.pv_P + (int64_t)tid * a.n + base, bytes, &s_bar);
+        for (int k = tid; k < 81; k += kEkfBlock) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
     } else if (valid) {
 #pragma unroll 9
         for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
@@ -153,11 +192,13 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         }
         acc[2] = acc[2] + 9.8f;
         for (int j = 0; j < 4; ++j) ang[j] = q[j];
-        sensor_fault(f, genv, 1, false, gyr, 3);
-        sensor_fault(f, genv, 3, true, ang, 4);
-        sensor_fault(f, genv, 4, false, acc, 3);
-        sensor_fault(f, genv, 5, false, pos, 3);
-        sensor_fault(f, genv, 6, false, vel, 3);
+        if (OZL_KEEP(1)) {
+            sensor_fault(f, genv, 1, false, gyr, 3);
+            sensor_fault(f, genv, 3, true, ang, 4);
+            sensor_fault(f, genv, 4, false, acc, 3);
+            sensor_fault(f, genv, 5, false, pos, 3);
+            sensor_fault(f, genv, 6, false, vel, 3);
+        }
         // ---- PV state: loads issued before the EKF arithmetic, consumed after it
         PVShared<kEkfBlock> pvs;
         pvs.P = s_P + tid;
@@ -167,7 +208,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         {
             const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
             const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
-            ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
+            if (OZL_KEEP(2)) ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
             for (int k = 0; k < 4; ++k) { a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
             for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4];
         }
@@ -176,13 +217,13 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             if (rst) { for (int k = 0; k < 3; ++k) { pvs.x[k] = p[k]; pvs.x[3 + k] = v[k]; pvs.x[6 + k] = 0.f; } }
             const float qt[4] = {q[3], q[0], q[1], q[2]};
             if (use_tma) mbar_wait(&s_bar, 0);                    // the covariance tile has landed
-            pv_predict(pvs, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
+            if (OZL_KEEP(4)) pv_predict(pvs, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
             // shared sensor-trigger counters (:425-440): the reference advances them once per env-iteration, i.e. the k-th
             // iteration overall is step * N_total + GLOBAL env id (invariant to how the envs are sharded over GPUs)
             const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n_total + (uint64_t)genv;
-            if (a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(pvs, pos, a.pos_var);
+            if (OZL_KEEP(8) && a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(pvs, pos, a.pos_var);
             const float zero3[3] = {0.f, 0.f, 0.f};
-            if (a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(pvs, vel, zero3);  // gps_var=None => R = 0
+            if (OZL_KEEP(8) && a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(pvs, vel, zero3);  // gps_var=None => R = 0
             for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = pvs.x[kk];
             for (int kk = 0; kk < 3; ++kk) { est_p[kk] = pvs.x[kk]; est_v[kk] = pvs.x[3 + kk]; }
         }
@@ -209,7 +250,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         // drain: every thread's filter writes are made visible to the async proxy, then 81 threads issue one plane store each
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid < 81) bulk_store_s2g(a.pv_P + (int64_t)tid * a.n + base, s_P + tid * kEkfBlock, (uint32_t)n_here * 4u);
+        for (int k = tid; k < 81; k += kEkfBlock) bulk_store_s2g(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, (uint32_t)n_here * 4u);
     }
     // the env's remaining planes for the step below: loads issued before the controller arithmetic (L2 hits by now)
     Loaded L;
@@ -220,7 +261,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     }
     float4 wr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        if (warm) {
+        if (warm || !OZL_KEEP(16)) {
             wr = make_float4(a.hover, 0.f, 0.f, 0.f);                                     // :526-528
         } else {
             float th, tq[3];
@@ -242,8 +283,10 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         Env e;
         unpack(L, e);
         const float act[4] = {wr.x, wr.y, wr.z, wr.w};
-        env_step(e, act, prog, rst, genv, step, c, o, ACT_WRENCH, tgt);
-        obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
+        if (OZL_KEEP(32)) {
+            env_step(e, act, prog, rst, genv, step, c, o, ACT_WRENCH, tgt);
+            obs_epilogue(o.obs, genv, step, flicker_blackout(step, c), c);
+        }
         store_dynamic(pl, i, e);
         store_static(pl, i, e);
         io.rew[i] = o.rew;
@@ -268,25 +311,32 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     // step counter: the launch retires one unit per 128-env tile in total -- block b accounts for the tiles that END in its env range
     const unsigned long long units = (unsigned long long)((base + n_here + kTile - 1) / kTile - (base + kTile - 1) / kTile);
     block_epilogue<kEkfBlock>(c, pl, valid, o, n_here, units + (blockIdx.x == 0 ? (unsigned long long)c.step_pad : 0ull));
-    if (tid == 0) bulk_wait_read_all();
+    // release the tile (tile_chain.cuh): every bulk store of this CTA has completed, every thread's plain stores are ordered
+    // before the barrier, then one fence + release store by the leader
+    if (!chain_words) {
+        if (tid == 0) bulk_wait_read_all();
+        return;
+    }
+    if (tid < 81) { bulk_wait_all(); fence_proxy_async_all(); }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release_u64(seq + 1, step + 1ull); }
 }
 
 }  // namespace ozl
 
 using namespace ozl;
 
-// Envs per CTA of the fused kernel.  Every choice keeps 512 env-threads resident per SM; OZL_EKF_BLOCK (128 / 256 / 512) overrides
-// the default for experiments.
+// Envs per CTA of the fused kernel (default 96, see above); OZL_EKF_BLOCK (64 / 96 / 128 / 256 / 512) overrides it for experiments.
 static int ozl_ekf_lee_block(const ozl_env* env, int64_t n) {
     static int forced = -1;
     if (forced < 0) {
         const char* v = getenv("OZL_EKF_BLOCK");
         forced = v ? atoi(v) : 0;
-        if (forced != 0 && forced != 128 && forced != 256 && forced != 512) forced = 0;
+        if (forced != 0 && forced != 64 && forced != 96 && forced != 128 && forced != 256 && forced != 512) forced = 0;
     }
     if (forced) return forced;
     (void)env; (void)n;
-    return 128;
+    return 96;
 }
 
 static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_husky_args* husky, const StepIo io, void* stream) {
@@ -327,9 +377,26 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
         if (io.reset != a.reset || (h.reset && h.reset != a.reset))
             return set_error("ozl_ekf_lee_landed_step: the estimator, the vehicle and the step must see the same reset buffer");
     }
+    // tile-chained launches (tile_chain.cuh): chain only behind the previous chained launch of this handle in the SAME stream
+    // capture, with nothing captured in between (the stream's one dependency is that launch's node)
+    // Chaining pays when the grid is several waves long (262144 envs: 125 -> 110 us per step); a ONE-wave grid runs in lockstep
+    // either way and only pays the protocol's latency (65536 envs: 27.2 -> 33 us), so it keeps the classic launch (chain = -1).
     const int block = ozl_ekf_lee_block(env, a.n);
     const unsigned grid = (unsigned)((a.n + block - 1) / block);
     const size_t smem = (size_t)81 * block * sizeof(float);
+    const long long slots = (long long)env->sm_count * ekf_minb(block);
+    const bool may_chain = husky && env->use_pdl && (env->chain_mode == 2 || (env->chain_mode == 1 && (long long)grid > slots));
+    int chain = may_chain ? 0 : -1;
+    if (may_chain && env->chain_last_node) {
+        cudaStreamCaptureStatus cs; unsigned long long cid = 0; size_t nd = 0;
+        const cudaGraphNode_t* deps = nullptr;
+        if (cudaStreamGetCaptureInfo_v3((cudaStream_t)stream, &cs, &cid, nullptr, &deps, nullptr, &nd) == cudaSuccess) {
+            if (cs == cudaStreamCaptureStatusActive && cid == env->chain_capture_id && nd == 1 && (void*)deps[0] == env->chain_last_node)
+                chain = 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
     int rc;
 #define OZL_LAUNCH_EKF(B, WS)                                                                                                   \
     do {                                                                                                                        \
@@ -340,15 +407,27 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
             attr_set = true;                                                                                                    \
         }                                                                                                                       \
         rc = launch_pdl_smem(env, ekf_lee_fused_kernel<B, WS>, dim3(grid), dim3(B), smem, (cudaStream_t)stream, env->dev,       \
-                             env->pl, a, use_tma, h, io);                                                                       \
+                             env->pl, a, use_tma, h, io, chain);                                                                \
     } while (0)
     if (husky) {
-        if (block == 512) OZL_LAUNCH_EKF(512, true); else if (block == 256) OZL_LAUNCH_EKF(256, true); else OZL_LAUNCH_EKF(128, true);
+        if (block == 512) OZL_LAUNCH_EKF(512, true); else if (block == 256) OZL_LAUNCH_EKF(256, true);
+        else if (block == 64) OZL_LAUNCH_EKF(64, true); else if (block == 128) OZL_LAUNCH_EKF(128, true); else OZL_LAUNCH_EKF(96, true);
     } else {
-        if (block == 512) OZL_LAUNCH_EKF(512, false); else if (block == 256) OZL_LAUNCH_EKF(256, false); else OZL_LAUNCH_EKF(128, false);
+        if (block == 512) OZL_LAUNCH_EKF(512, false); else if (block == 256) OZL_LAUNCH_EKF(256, false);
+        else if (block == 128) OZL_LAUNCH_EKF(128, false); else OZL_LAUNCH_EKF(96, false);
     }
 #undef OZL_LAUNCH_EKF
     if (rc) return check_cuda(cudaGetLastError(), "ekf_lee_fused_kernel");
+    if (may_chain) {       // remember the node this launch became (if it was captured): the next launch may chain behind it
+        cudaStreamCaptureStatus cs; unsigned long long cid = 0; size_t nd = 0;
+        const cudaGraphNode_t* deps = nullptr;
+        env->chain_last_node = nullptr;
+        if (cudaStreamGetCaptureInfo_v3((cudaStream_t)stream, &cs, &cid, nullptr, &deps, nullptr, &nd) == cudaSuccess) {
+            if (cs == cudaStreamCaptureStatusActive && nd == 1) { env->chain_capture_id = cid; env->chain_last_node = (void*)deps[0]; }
+        } else {
+            cudaGetLastError();
+        }
+    }
     return 0;
 }
 

@@ -35,6 +35,7 @@ struct Planes {
     int64_t plane4, plane2;     // OZL_TILED=0: byte strides of the float4 / float2 planes
     unsigned long long* ctrl;   // [0..2] step-counter record {base, units, shift} (step_counter.cuh), [4] TMA-kernel tile scheduler (monotonic)
     double* metrics;            // kMetricSlots x kMetricStride
+    unsigned long long* tile_seq;   // [tiles][2] {started, done}: per-tile step sequence of the tile-chained launches (tile_chain.cuh)
 };
 // k = 0..3: d0..d3, k = 4..6: s0..s2
 __device__ __forceinline__ float4* plane4_ptr(const Planes& pl, int k, int64_t i) {
@@ -72,6 +73,10 @@ struct ozl_env {
     volatile unsigned int* host_done;   // cudaHostAlloc'ed, one word
     unsigned int host_seq;              // sequence number of the last host step launched
     int use_host_flag;                  // OZL_HOST_FLAG=0 turns the completion word off (stream synchronise instead)
+    // tile-chained step launches (tile_chain.cuh): the graph node of the last chained launch captured on this handle
+    int chain_mode;                     // OZL_EKF_CHAIN: 0 = never chain, 1 = chain launches that are provably adjacent in a stream capture
+    unsigned long long chain_capture_id;
+    void* chain_last_node;
 };
 
 // Step launches go through cudaLaunchKernelEx so that they can carry the programmatic-stream-serialization attribute (PDL):

@@ -739,14 +739,22 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     const size_t plane4 = align_up(tiles * kTile * sizeof(float4), 256), plane2 = align_up(tiles * kTile * sizeof(float2), 256);
     const size_t state = OZL_TILED ? align_up(tiles * (size_t)kTileBytes, 256) : 7 * plane4 + plane2;
     const size_t ctrl = 256, metrics = align_up(sizeof(double) * kMetricSlots * kMetricStride, 256);
-    e->arena_bytes = state + ctrl + metrics;
+    const size_t tile_seq = align_up(tiles * 4 * sizeof(unsigned long long), 256);    // {started, done} per CTA of >= 64 envs
+    e->arena_bytes = state + ctrl + metrics + tile_seq;
     if (check_cuda(cudaMalloc(&e->arena, e->arena_bytes), "cudaMalloc(state arena)")) { delete e; return 1; }
     if (check_cuda(cudaMemset(e->arena, 0, e->arena_bytes), "cudaMemset(state arena)")) { cudaFree(e->arena); delete e; return 1; }
     char* p = (char*)e->arena;
     e->pl.base = p; e->pl.plane4 = (int64_t)plane4; e->pl.plane2 = (int64_t)plane2;
     p += state;
     e->pl.ctrl = (unsigned long long*)p; p += ctrl;
-    e->pl.metrics = (double*)p;
+    e->pl.metrics = (double*)p; p += metrics;
+    e->pl.tile_seq = (unsigned long long*)p;
+    {
+        const char* cv = getenv("OZL_EKF_CHAIN");
+        e->chain_mode = cv ? atoi(cv) : 1;
+        e->chain_capture_id = 0;
+        e->chain_last_node = nullptr;
+    }
     {
         const char* hv = getenv("OZL_HOST_FLAG");
         e->use_host_flag = hv ? atoi(hv) : 1;

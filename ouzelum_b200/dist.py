@@ -92,3 +92,85 @@ def summarize(metrics: torch.Tensor):
     return {"env_steps": m[8], "episodes": m[9], "mean_reward": m[0] / steps, "mean_episode_return": m[1] / eps,
             "mean_episode_length": m[10] / eps, "timeouts": m[11], "crash_dist": m[12], "crash_z": m[13],
             "fault_active_frac": m[14] / steps, "landed_episodes": m[2], "resets": m[15]}
+
+
+class PeerMetrics:
+    """Sum of the 16-double metrics vector over all ranks through NVLink peer memory (csrc/peer_metrics.cu): every rank's
+    metrics-read kernel stores its values straight into every peer's mailbox; no NCCL kernel, no side stream, CUDA-graph
+    capturable.  One process per GPU (`torch.distributed` only carries the 64-byte IPC handles at start-up), or several devices
+    driven by one process (`connect_same_process`).
+
+        pm = PeerMetrics(device)                  # after init_process_group(...)
+        pm.push(sim, prev_sum=buf16)              # every few steps: one launch; buf16 <- sum of the PREVIOUS exchange
+        pm.sum(sim, out=buf16)                    # when the reduced vector of the last push is needed
+    """
+
+    def __init__(self, device, rank=None, world=None, connect=True):
+        import ctypes as C
+        from ._lib import check, lib
+        self.device = torch.device(device)
+        have_pg = dist.is_available() and dist.is_initialized()
+        self.rank = int(rank if rank is not None else (dist.get_rank() if have_pg else 0))
+        self.world = int(world if world is not None else (dist.get_world_size() if have_pg else 1))
+        h = C.c_void_p()
+        check(lib.ozl_metrics_xchg_create(self.rank, self.world, self.device.index or 0, C.byref(h)))
+        self._h = h
+        if connect and self.world > 1:
+            self._connect_ipc()
+
+    def _connect_ipc(self):
+        import ctypes as C
+        from ._lib import check, lib
+        mine = (C.c_ubyte * 64)()
+        check(lib.ozl_metrics_xchg_ipc_handle(self._h, mine))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(mine))          # host-side, once: plumbing
+        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(gathered))
+        check(lib.ozl_metrics_xchg_connect_ipc(self._h, blob))
+        dist.barrier()                                         # every mailbox is mapped before anyone pushes
+
+    @staticmethod
+    def connect_same_process(exchanges):
+        """Several devices driven by ONE process: enable peer access and hand every exchange the others' mailboxes."""
+        import ctypes as C
+        from ._lib import check, lib
+        boxes = (C.c_void_p * len(exchanges))()
+        devs = (C.c_int32 * len(exchanges))()
+        for i, e in enumerate(exchanges):
+            b = C.c_void_p()
+            check(lib.ozl_metrics_xchg_box(e._h, C.byref(b)))
+            boxes[i], devs[i] = b.value, e.device.index or 0
+        for e in exchanges:
+            check(lib.ozl_metrics_xchg_connect_ptrs(e._h, boxes, devs))
+
+    def push(self, sim, local=None, prev_sum=None, clear=False):
+        from ._lib import check, lib, ptr
+        check(lib.ozl_metrics_push(sim._h, self._h, ptr(local), ptr(prev_sum), 1 if clear else 0,
+                                   torch._C._cuda_getCurrentRawStream(self.device.index or 0)))
+
+    def sum(self, sim, out=None):
+        from ._lib import check, lib
+        if out is None:
+            out = torch.zeros(16, dtype=torch.float64, device=self.device)
+        check(lib.ozl_metrics_sum(sim._h, self._h, out.data_ptr(), torch._C._cuda_getCurrentRawStream(self.device.index or 0)))
+        return out
+
+    def status(self):
+        import ctypes as C
+        from ._lib import check, lib
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.ozl_metrics_xchg_status(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                          torch._C._cuda_getCurrentRawStream(self.device.index or 0)))
+        return {"pushed": a.value, "summed": b.value, "error": c.value}
+
+    def close(self):
+        from ._lib import lib
+        if getattr(self, "_h", None):
+            lib.ozl_metrics_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -116,3 +116,60 @@ def test_shared_trigger_counters_are_shard_invariant():
         assert torch.equal(o["obs"], torch.cat([o1["obs"], o2["obs"]])), t
         assert torch.equal(r, torch.cat([r1, r2])) and torch.equal(d, torch.cat([d1, d2])), t
     assert torch.equal(full.pvfilters.get_states(), torch.cat([lo.pvfilters.get_states(), hi.pvfilters.get_states()]))
+
+
+@pytest.mark.parametrize("n", [65536, 4099, 300])
+def test_tile_chained_graph_replay_equals_eager_steps(n, monkeypatch):
+    """Steps captured back to back into one CUDA graph are launched TILE-CHAINED (csrc/tile_chain.cuh: launch L+1's CTA b waits only
+    for launch L's CTA b, not for the whole grid, so consecutive launches overlap).  The replay must leave every buffer exactly as
+    the same number of eager (classic, fully ordered) launches does: env planes, filter banks, glue buffers, surface tensors,
+    episode statistics and the step counter -- over several replays, with eager steps in between (the first launch of every
+    replay re-derives the tile sequence from the global step record)."""
+    import ouzelum_b200
+    monkeypatch.setenv("OZL_EKF_CHAIN", "2")      # chain one-wave grids too (the default chains only grids longer than one wave)
+    mk = lambda: ouzelum_b200.make(
+        seed=3, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
+        cfg=ouzelum_b200.task_config("EKFLeeLanded", n, seed=3, POMDP="random_noise", pomdp_prob=0.15, ConvergenceTime=5,
+                                     domainRandomization={"enable": True}, rotorFault={"enable": True}, maxEpisodeLength=11))
+    eager, graphed = mk(), mk()
+    a = torch.zeros(n, 4, device=DEV)
+    K = 17
+    for e in (eager, graphed):
+        for _ in range(3):
+            e.step(a)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(K):
+            graphed._launch(a)
+    torch.cuda.synchronize()
+    # the capture itself launched nothing: bring the host-side step count back
+    graphed.sim_step_count -= K
+
+    def same(tag):
+        torch.cuda.synchronize()
+        se, sg = eager.sim.get_state(), graphed.sim.get_state()
+        for k_ in se:
+            assert torch.equal(se[k_], sg[k_]), f"{tag}: sim state {k_}"
+        pe, pg = eager.sim.get_params(), graphed.sim.get_params()
+        assert torch.equal(pe[0], pg[0]) and torch.equal(pe[1], pg[1]), f"{tag}: params"
+        for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "prev_root_linvels", "target_waypoints", "_wrench"):
+            assert torch.equal(getattr(eager, name), getattr(graphed, name)), f"{tag}: {name}"
+        assert torch.equal(eager.ekf._q, graphed.ekf._q) and torch.equal(eager.ekf._P, graphed.ekf._P), f"{tag}: EKF"
+        assert torch.equal(eager.pvfilters._x, graphed.pvfilters._x), f"{tag}: PV state"
+        assert torch.equal(eager.pvfilters._P, graphed.pvfilters._P), f"{tag}: PV covariance"
+        assert torch.equal(eager.husky.target, graphed.husky.target), f"{tag}: vehicle"
+        me, mg = eager.sim.metrics().cpu(), graphed.sim.metrics().cpu()
+        assert torch.equal(me[[2, 8, 9, 10, 11, 12, 13, 14, 15]], mg[[2, 8, 9, 10, 11, 12, 13, 14, 15]]), f"{tag}: integer metrics"
+        assert eager.sim.step_count == graphed.sim.step_count, f"{tag}: step counter"
+
+    for rep in range(3):
+        g.replay()
+        graphed.sim_step_count += K
+        for _ in range(K):
+            eager._launch(a)
+        same(f"replay {rep}")
+        for e in (eager, graphed):            # eager steps between replays
+            e.step(a)
+            e.step(a)
+        same(f"eager after replay {rep}")
+    assert eager.episodes > 0
