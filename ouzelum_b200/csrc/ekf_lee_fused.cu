@@ -23,7 +23,11 @@
 #ifndef OZL_ABLATE
 #define OZL_ABLATE 0
 #endif
-#define OZL_KEEP(bit) (!(OZL_ABLATE & (bit)))   // 1 sensor faults, 2 EKF, 4 PV predict, 8 PV fixes, 16 Lee controller, 32 env step
+#define OZL_KEEP(bit) (!(OZL_ABLATE & (bit)))
+#ifndef OZL_PV_COOP
+#define OZL_PV_COOP 1       // warp-cooperative PV fixes (filters.cuh, pv_correct_coop); 0 = every thread runs its own fixes
+#endif
+constexpr int kEkfSmemRows = 81 + (OZL_PV_COOP ? 12 : 0);   // covariance tile (+ the cooperative fixes' scratch columns), floats per env   // 1 sensor faults, 2 EKF, 4 PV predict, 8 PV fixes, 16 Lee controller, 32 env step
 
 namespace ozl {
 
@@ -92,6 +96,9 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     const int64_t i = base + tid;
     const bool valid = i < a.n;
     const int n_here = (a.n - base) < kEkfBlock ? (int)(a.n - base) : kEkfBlock;
+    // valid lanes of this warp (a prefix): the participants of the warp-cooperative PV fixes
+    const int wl = n_here - (tid & ~31);
+    const unsigned wmask = wl >= 32 ? 0xffffffffu : (wl > 0 ? (1u << wl) - 1u : 0u);
     if (tid == 0 && use_tma) mbar_init(&s_bar, 1);
     // tile-chained launches (tile_chain.cuh): chained == this launch does NOT wait for the previous grid, only for its own tile
     // chain: -1 classic launch (no tile words touched), 0 first launch of a chain, 1 chained
@@ -221,9 +228,18 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             // shared sensor-trigger counters (:425-440): the reference advances them once per env-iteration, i.e. the k-th
             // iteration overall is step * N_total + GLOBAL env id (invariant to how the envs are sharded over GPUs)
             const uint64_t k = a.per_env_triggers ? step : step * (uint64_t)a.n_total + (uint64_t)genv;
-            if (OZL_KEEP(8) && a.pos_period && (k % a.pos_period) == a.pos_phase) pv_correct<0>(pvs, pos, a.pos_var);
-            const float zero3[3] = {0.f, 0.f, 0.f};
-            if (OZL_KEEP(8) && a.vel_period && (k % a.vel_period) == a.vel_phase) pv_correct<3>(pvs, vel, zero3);  // gps_var=None => R = 0
+            const bool fix_pos = OZL_KEEP(8) && a.pos_period && (k % a.pos_period) == a.pos_phase;
+            const bool fix_vel = OZL_KEEP(8) && a.vel_period && (k % a.vel_period) == a.vel_phase;
+            const float zero3[3] = {0.f, 0.f, 0.f};                                                  // gps_var=None => R = 0
+#if OZL_PV_COOP
+            // warp-cooperative fixes (filters.cuh): first fix of every env, then the velocity fix of the envs that had both
+            float* const scr = s_P + 81 * kEkfBlock + tid;
+            pv_correct_coop(pvs, scr, wmask, tid & 31, fix_pos ? 0 : (fix_vel ? 3 : -1), fix_pos ? pos : vel, a.pos_var, zero3);
+            pv_correct_coop(pvs, scr, wmask, tid & 31, (fix_pos && fix_vel) ? 3 : -1, vel, a.pos_var, zero3);
+#else
+            if (fix_pos) pv_correct<0>(pvs, pos, a.pos_var);
+            if (fix_vel) pv_correct<3>(pvs, vel, zero3);
+#endif
             for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = pvs.x[kk];
             for (int kk = 0; kk < 3; ++kk) { est_p[kk] = pvs.x[kk]; est_v[kk] = pvs.x[3 + kk]; }
         }
@@ -383,7 +399,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     // either way and only pays the protocol's latency (65536 envs: 27.2 -> 33 us), so it keeps the classic launch (chain = -1).
     const int block = ozl_ekf_lee_block(env, a.n);
     const unsigned grid = (unsigned)((a.n + block - 1) / block);
-    const size_t smem = (size_t)81 * block * sizeof(float);
+    const size_t smem = (size_t)kEkfSmemRows * block * sizeof(float);
     const long long slots = (long long)env->sm_count * ekf_minb(block);
     const bool may_chain = husky && env->use_pdl && (env->chain_mode == 2 || (env->chain_mode == 1 && (long long)grid > slots));
     int chain = may_chain ? 0 : -1;
@@ -403,7 +419,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
         static bool attr_set = false;                                                                                           \
         if (!attr_set) {                                                                                                        \
             if (check_cuda(cudaFuncSetAttribute(ekf_lee_fused_kernel<B, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                                81 * B * (int)sizeof(float)), "cudaFuncSetAttribute")) return 1;               \
+                                                kEkfSmemRows * B * (int)sizeof(float)), "cudaFuncSetAttribute")) return 1;     \
             attr_set = true;                                                                                                    \
         }                                                                                                                       \
         rc = launch_pdl_smem(env, ekf_lee_fused_kernel<B, WS>, dim3(grid), dim3(B), smem, (cudaStream_t)stream, env->dev,       \

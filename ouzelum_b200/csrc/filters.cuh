@@ -86,33 +86,55 @@ __device__ __forceinline__ void pv_predict(PVShared<STRIDE>& s, const float acc[
             s.at(3 + i, c) = fmaf(dt, rb, rv);
         }
     }
-    // ---- N = M F^T, one row per iteration
-    OZL_PV_LOOP
-    for (int r = 0; r < 9; ++r) {
-        float mp[3], mv[3], mb[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { mp[j] = s.at(r, j); mv[j] = s.at(r, 3 + j); mb[j] = s.at(r, 6 + j); }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float rv = dot3(R[i][0], R[i][1], R[i][2], mv), rb = dot3(R[i][0], R[i][1], R[i][2], mb);
-            s.at(r, i) = fmaf(hdt2, rb, fmaf(dt, rv, mp[i]));
-            s.at(r, 3 + i) = fmaf(dt, rb, rv);
-        }
-    }
-    // ---- + G Q G^T = [hdt2; dt] (R Q R^T) [hdt2; dt]^T on the p/v blocks
-    const float k_pp = hdt2 * hdt2, k_pv = hdt2 * dt, k_vv = dt * dt;
+    // ---- process noise G Q G^T = [hdt2; dt] (R Q R^T) [hdt2; dt]^T on the p/v blocks: C = R Q R^T here, added to each entry right
+    //      after the row of N it belongs to has been formed (same operation on the same value as a separate read-modify-write
+    //      sweep over the 36 entries, without the 36 loads and stores)
+    float C[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float rq[3] = {R[i][0] * acc_var[0], R[i][1] * acc_var[1], R[i][2] * acc_var[2]};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float cij = dot3(rq[0], rq[1], rq[2], R[j]);
-            s.at(i, j) = fmaf(k_pp, cij, s.at(i, j));
-            s.at(i, 3 + j) = fmaf(k_pv, cij, s.at(i, 3 + j));
-            s.at(3 + i, j) = fmaf(k_pv, cij, s.at(3 + i, j));
-            s.at(3 + i, 3 + j) = fmaf(k_vv, cij, s.at(3 + i, 3 + j));
+        for (int j = 0; j < 3; ++j) C[i][j] = dot3(rq[0], rq[1], rq[2], R[j]);
+    }
+    const float k_pp = hdt2 * hdt2, k_pv = hdt2 * dt, k_vv = dt * dt;
+    // ---- N = M F^T, one row per iteration, rows in three groups (p, v, b); the group index is uniform
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+        const float kA = g == 0 ? k_pp : k_pv, kB = g == 0 ? k_pv : k_vv;      // (p,p)/(p,v) for the p rows, (v,p)/(v,v) for the v rows
+#pragma unroll
+        for (int ri = 0; ri < 3; ++ri) {
+            const int r = g * 3 + ri;
+            float mp[3], mv[3], mb[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { mp[j] = s.at(r, j); mv[j] = s.at(r, 3 + j); mb[j] = s.at(r, 6 + j); }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float rv = dot3(R[i][0], R[i][1], R[i][2], mv), rb = dot3(R[i][0], R[i][1], R[i][2], mb);
+                float np = fmaf(hdt2, rb, fmaf(dt, rv, mp[i])), nv = fmaf(dt, rb, rv);
+                if (g < 2) { np = fmaf(kA, C[ri][i], np); nv = fmaf(kB, C[ri][i], nv); }
+                s.at(r, i) = np;
+                s.at(r, 3 + i) = nv;
+            }
         }
     }
+}
+
+// 3x3 inverse by the adjugate, evaluated in float64 and rounded to float32 once.  After the first fix P[H,H] is of the order of
+// R = 1e-7 with strongly correlated entries; the float32 adjugate loses most of its digits to cancellation there (the reference's
+// torch.linalg.inv is a pivoted LU), and the innovation gain inherits the error (measured against a float64 evaluation of the
+// whole step: 1.7e-4 of the state scale with the float32 adjugate, 1e-7 for the reference).
+__device__ __forceinline__ void pv_inverse3(const float S[3][3], float Si[3][3]) {
+    const double s00 = S[0][0], s01 = S[0][1], s02 = S[0][2], s10 = S[1][0], s11 = S[1][1], s12 = S[1][2];
+    const double s20 = S[2][0], s21 = S[2][1], s22 = S[2][2];
+    const double c00 = fma(s11, s22, -(s12 * s21)), c01 = fma(s12, s20, -(s10 * s22)), c02 = fma(s10, s21, -(s11 * s20));
+    const double id = 1.0 / fma(s02, c02, fma(s01, c01, s00 * c00));
+    Si[0][0] = (float)(c00 * id); Si[1][0] = (float)(c01 * id); Si[2][0] = (float)(c02 * id);
+    Si[0][1] = (float)(fma(s02, s21, -(s01 * s22)) * id);
+    Si[1][1] = (float)(fma(s00, s22, -(s02 * s20)) * id);
+    Si[2][1] = (float)(fma(s01, s20, -(s00 * s21)) * id);
+    Si[0][2] = (float)(fma(s01, s12, -(s02 * s11)) * id);
+    Si[1][2] = (float)(fma(s02, s10, -(s00 * s12)) * id);
+    Si[2][2] = (float)(fma(s00, s11, -(s01 * s10)) * id);
 }
 
 // correction_step (PVFilter.py:67-110) on block H = [LO, LO+3):
@@ -135,48 +157,117 @@ __device__ __forceinline__ void pv_correct(PVShared<STRIDE>& s, const float z[3]
     // reference's torch.linalg.inv is a pivoted LU), and the innovation gain inherits the error (measured against a float64
     // evaluation of the whole step: 1.7e-4 of the state scale with the float32 adjugate, 1e-7 for the reference).
     float Si[3][3];
-    {
-        const double s00 = S[0][0], s01 = S[0][1], s02 = S[0][2], s10 = S[1][0], s11 = S[1][1], s12 = S[1][2];
-        const double s20 = S[2][0], s21 = S[2][1], s22 = S[2][2];
-        const double c00 = fma(s11, s22, -(s12 * s21)), c01 = fma(s12, s20, -(s10 * s22)), c02 = fma(s10, s21, -(s11 * s20));
-        const double id = 1.0 / fma(s02, c02, fma(s01, c01, s00 * c00));
-        Si[0][0] = (float)(c00 * id); Si[1][0] = (float)(c01 * id); Si[2][0] = (float)(c02 * id);
-        Si[0][1] = (float)(fma(s02, s21, -(s01 * s22)) * id);
-        Si[1][1] = (float)(fma(s00, s22, -(s02 * s20)) * id);
-        Si[2][1] = (float)(fma(s01, s20, -(s00 * s21)) * id);
-        Si[0][2] = (float)(fma(s01, s12, -(s02 * s11)) * id);
-        Si[1][2] = (float)(fma(s02, s10, -(s00 * s12)) * id);
-        Si[2][2] = (float)(fma(s00, s11, -(s01 * s10)) * id);
+    pv_inverse3(S, Si);
+    const float inn[3] = {z[0] - s.x[LO], z[1] - s.x[LO + 1], z[2] - s.x[LO + 2]};     // from the OLD state, before any row updates x
+    // one row of K, x and P per iteration: row i of K needs only row i of the old P, read before the row is overwritten.
+    // Rows in three groups of three (p, v, b): the group index is uniform, so "is this row in H" and "which x entries does this
+    // group update" are branches, not per-element selects.
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+        const bool inH = (g * 3 == LO);
+        float dxg[3];
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii) {
+            const int i = g * 3 + ii;
+            float row[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) row[j] = s.at(i, j);
+            float K[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) K[j] = fmaf(row[LO + 2], Si[2][j], fmaf(row[LO + 1], Si[1][j], row[LO] * Si[0][j]));
+            dxg[ii] = fmaf(K[2], inn[2], fmaf(K[1], inn[1], K[0] * inn[0]));
+            // P <- IKH @ P with IKH = I, IKH[:,H] -= K  (PVFilter.py:88-89 / 108-109)
+            float w[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[k] = ((inH && ii == k) ? 1.0f : 0.0f) - K[k];
+            if (inH) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) s.at(i, j) = fmaf(w[2], PH[2][j], fmaf(w[1], PH[1][j], w[0] * PH[0][j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) s.at(i, j) = row[j] + fmaf(w[2], PH[2][j], fmaf(w[1], PH[1][j], w[0] * PH[0][j]));
+            }
+        }
+        if (g == 0) { s.x[0] += dxg[0]; s.x[1] += dxg[1]; s.x[2] += dxg[2]; }
+        else if (g == 1) { s.x[3] += dxg[0]; s.x[4] += dxg[1]; s.x[5] += dxg[2]; }
+        else { s.x[6] += dxg[0]; s.x[7] += dxg[1]; s.x[8] += dxg[2]; }
     }
-    const float inn[3] = {z[0] - s.x[LO], z[1] - s.x[LO + 1], z[2] - s.x[LO + 2]};
-    // one row of K, x and P per iteration: row i of K needs only row i of the old P, read before the row is overwritten
-    float xn[9];
+}
+
+// Warp-cooperative correction_step.  With the reference's SHARED trigger counters (ekf_lee_landed.py:425-440) the position fix
+// fires for one env in 7 and the velocity fix for one in 3, so a warp that runs pv_correct<0> and pv_correct<3> one after the
+// other works at 14 % and 33 % lane utilisation for ~1500 of its ~7000 instructions.  Here the lanes of a warp share the work:
+//   * `job` per lane: -1 none, 0 position fix, 3 velocity fix (block H = [job, job + 3)); the caller makes two passes (first fix
+//     of every env, then the velocity fix of the envs that had both);
+//   * every job gets S = min(9, lanes / jobs) worker lanes; worker `sub` of a job updates rows sub, sub + S, ... of the OWNER's
+//     covariance column in shared memory (rows are independent given the old rows of H, which every worker reads -- a broadcast --
+//     before the warp barrier that precedes the first write) and leaves the row's state increment in a 9-float scratch column;
+//   * the owner publishes its innovation z - x[H] in a 3-float scratch column before, and adds the increments to x after.
+// The arithmetic of a row is exactly pv_correct<LO>'s (same fused operations on the same operands in the same order; LO becomes a
+// per-lane value), so the cooperative and the per-thread form give identical bits.
+// scr: [12][STRIDE] floats of shared memory (rows 0-2 innovation, 3-11 increments), indexed like the covariance tile.
+template <int STRIDE>
+__device__ __forceinline__ void pv_correct_coop(PVShared<STRIDE>& s, float* scr_col, const unsigned wmask, const int lane, const int job,
+                                                const float z[3], const float rvar_pos[3], const float rvar_vel[3]) {
+    const unsigned busy = __ballot_sync(wmask, job >= 0);
+    if (busy == 0u) return;                                  // uniform
+    const int njobs = __popc(busy), nl = __popc(wmask);
+    int S = nl / njobs;
+    S = S > 9 ? 9 : S;
+    if (job >= 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) xn[i] = s.x[i];
-    OZL_PV_LOOP
-    for (int i = 0; i < 9; ++i) {
-        float row[9];
+        for (int k = 0; k < 3; ++k) scr_col[k * STRIDE] = z[k] - (job ? s.x[3 + k] : s.x[k]);
+    }
+    const int wrank = __popc(wmask & ((1u << lane) - 1u));
+    const int jidx = wrank / S, sub = wrank - jidx * S;
+    const bool working = jidx < njobs;
+    const int owner = working ? (int)__fns(busy, 0, jidx + 1) : lane;
+    const int LO = __shfl_sync(wmask, job, owner);
+    __syncwarp(wmask);                                       // innovations are published
+    float* const Pc = s.P + (owner - lane);                  // the owner's column of the covariance tile
+    float* const sc = scr_col + (owner - lane);
+    float PH[3][9], Si[3][3], inn[3] = {0.f, 0.f, 0.f};
+    if (working) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) row[j] = s.at(i, j);
-        float K[3];
+        for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) K[j] = fmaf(row[LO + 2], Si[2][j], fmaf(row[LO + 1], Si[1][j], row[LO] * Si[0][j]));
-        const float dx = fmaf(K[2], inn[2], fmaf(K[1], inn[1], K[0] * inn[0]));
+            for (int j = 0; j < 9; ++j) PH[k][j] = Pc[((LO + k) * 9 + j) * STRIDE];
 #pragma unroll
-        for (int ii = 0; ii < 9; ++ii) xn[ii] = (ii == i) ? xn[ii] + dx : xn[ii];      // select chain: no dynamic register index
-        // P <- IKH @ P with IKH = I, IKH[:,H] -= K  (PVFilter.py:88-89 / 108-109)
-        float w[3];
+        for (int k = 0; k < 3; ++k) inn[k] = sc[k * STRIDE];
+        float Sm[3][3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = ((i == LO + k) ? 1.0f : 0.0f) - K[k];
-        const bool inH = (i >= LO) && (i < LO + 3);
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const float acc3 = fmaf(w[2], PH[2][j], fmaf(w[1], PH[1][j], w[0] * PH[0][j]));
-            s.at(i, j) = inH ? acc3 : (row[j] + acc3);
+            for (int j = 0; j < 3; ++j) Sm[i][j] = (LO ? PH[i][3 + j] : PH[i][j]) + (i == j ? (LO ? rvar_vel[i] : rvar_pos[i]) : 0.f);
+        pv_inverse3(Sm, Si);
+    }
+    __syncwarp(wmask);                                       // every worker holds the old rows of H: rows may be overwritten now
+    if (working) {
+        for (int i = sub; i < 9; i += S) {
+            float row[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) row[j] = Pc[(i * 9 + j) * STRIDE];
+            const float r0 = LO ? row[3] : row[0], r1 = LO ? row[4] : row[1], r2 = LO ? row[5] : row[2];
+            float K[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) K[j] = fmaf(r2, Si[2][j], fmaf(r1, Si[1][j], r0 * Si[0][j]));
+            sc[(3 + i) * STRIDE] = fmaf(K[2], inn[2], fmaf(K[1], inn[1], K[0] * inn[0]));
+            float w[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[k] = ((i == LO + k) ? 1.0f : 0.0f) - K[k];
+            const bool inH = (i >= LO) && (i < LO + 3);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const float acc3 = fmaf(w[2], PH[2][j], fmaf(w[1], PH[1][j], w[0] * PH[0][j]));
+                Pc[(i * 9 + j) * STRIDE] = inH ? acc3 : (row[j] + acc3);
+            }
         }
     }
+    __syncwarp(wmask);                                       // increments are published
+    if (job >= 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) s.x[i] = xn[i];
+        for (int i = 0; i < 9; ++i) s.x[i] += scr_col[(3 + i) * STRIDE];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2: attitude EKF
