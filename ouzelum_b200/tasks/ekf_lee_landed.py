@@ -43,6 +43,9 @@ class EKFLeeLanded(_VehicleTargetTask):
         self.per_env_triggers = bool(env.get("perEnvSensorTriggers", False))
         self.fused = bool(env.get("fusedEstimator", True))      # one kernel for the whole estimator + controller chain
         self.fused_step = bool(env.get("fusedStep", True))      # ... and the vehicle + physics step in the same launch
+        # the fused kernels can also write the estimated state [N,13] and the controller command [N,4] they computed (inspection /
+        # parity tests: `_est`, `_cmd`); off by default -- 68 B per env of row-strided stores nobody on the step path reads
+        self.expose_estimates = bool(env.get("exposeEstimates", False))
         super().__init__(cfg, *a, **k)
 
     def _native_cfg(self):
@@ -82,7 +85,9 @@ class EKFLeeLanded(_VehicleTargetTask):
         a.pv_x9xN, a.pv_P81xN = self.pvfilters._x.data_ptr(), self.pvfilters._P.data_ptr()
         a.prev_linvel3, a.waypoint3 = self.prev_root_linvels.data_ptr(), self.target_waypoints.data_ptr()
         a.target3, a.reset, a.wrench4 = self.husky.target.data_ptr(), self.reset_buf.data_ptr() if hasattr(self, "reset_buf") else 0, self._wrench.data_ptr()
-        a.est13, a.cmd4, a.gains16 = self._est.data_ptr(), self._cmd.data_ptr(), self.controller._gains
+        a.est13 = self._est.data_ptr() if self.expose_estimates else None
+        a.cmd4 = self._cmd.data_ptr() if self.expose_estimates else None
+        a.gains16 = self.controller._gains
         a.dt, a.mg, a.hover_force = self.dt, self.mg, float(self._hover[0, 0].item())
         a.convergence_steps = int(self.ConvergenceTime)
         a.pomdp_mode, a.pomdp_prob = self._pomdp_mode, self._pomdp_prob

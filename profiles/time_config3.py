@@ -14,7 +14,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 DEV = "cuda:0"
 cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=0, POMDP="random_noise", pomdp_prob=0.15, ConvergenceTime=20,
-                               domainRandomization={"enable": True}, rotorFault={"enable": True})
+                               domainRandomization={"enable": True}, rotorFault={"enable": True},
+                               exposeEstimates=bool(int(os.environ.get("OZL_EXPOSE_EST", "0"))))
 env = ouzelum_b200.make(seed=0, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
 a = torch.zeros(n, 4, device=DEV)
 for _ in range(60):
@@ -35,6 +36,6 @@ for _ in range(5):
     e1.record()
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1) * 1e3 / steps)
-print(json.dumps({"lib": os.path.basename(os.environ.get("OUZELUM_B200_LIB", "in-tree")), "ekf_block": os.environ.get("OZL_EKF_BLOCK", "default"),
+print(json.dumps({"lib": os.path.basename(os.environ.get("OUZELUM_B200_LIB", "in-tree")), "expose_est": os.environ.get("OZL_EXPOSE_EST", "0"), "ekf_block": os.environ.get("OZL_EKF_BLOCK", "default"),
                   "n_envs": n, "us_per_step": best, "env_steps_per_sec": n / best * 1e6, "frac_of_hbm_1372B": 1372 * n / best / 1e3 / 6552.3,
                   "episodes": env.episodes, "landings": env.landings}), flush=True)

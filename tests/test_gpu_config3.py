@@ -38,7 +38,8 @@ def test_one_launch_ekf_lee_landed_step_vs_oracle(n, steps):
     from oracle.quad_step import QuadStepOracle
     conv, seed, sigma = 3, 12, 0.15
     cfg = ouzelum_b200.task_config("EKFLeeLanded", n, seed=seed, POMDP="random_noise", pomdp_prob=sigma, ConvergenceTime=conv,
-                                   domainRandomization={"enable": True}, rotorFault={"enable": True}, maxEpisodeLength=7)
+                                   domainRandomization={"enable": True}, rotorFault={"enable": True}, maxEpisodeLength=7,
+                                   exposeEstimates=True)        # the kernel also writes its estimate / command (`_est`, `_cmd`)
     env = ouzelum_b200.make(seed=seed, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True, cfg=cfg)
     assert env.fused and env.fused_step                       # the one-launch path
     phys = QuadStepOracle(env.native_cfg.to_dict())
