@@ -57,16 +57,15 @@ struct EkfLeeArgs {
 // with 16; 96-env CTAs spread the same envs as 4 or 5 CTAs (12 or 15 warps).  See ozl_ekf_lee_block().
 constexpr int ekf_minb(int block) { return block <= 64 ? 8 : (block <= 96 ? 5 : (block <= 128 ? 4 : (block <= 256 ? 2 : 1))); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA):
 //   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by 81 TMA bulk copies
-//     (one plane each, issued by 81 different threads, completing on one mbarrier) before anything else: the 41 KB of loads fly
+//     (one plane each, issued by different threads, completing on one mbarrier) before anything else: the 31 KB of loads fly
 //     while every thread runs the vehicle, the sensor front-end and the float64 attitude EKF out of registers
-//   * everything the later stages read from HBM (EKF / PV state planes, waypoint, the env's static planes, progress) is
-//     prefetched into L2 at the top, and each stage's loads are issued before the previous stage's arithmetic, so no stage
-//     starts with a DRAM round trip on its critical path (round 1: 21 % of the stall samples were `long_scoreboard`)
-//   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared)
+//   * each stage's loads are issued before the previous stage's arithmetic.  (Round 2 also prefetched everything the later stages
+//     read into L2 at the top; with the state L2-resident in steady state -- profiles/r02q_steady_state_dram_traffic.json -- the
+//     ~40 prefetch instructions per thread only cost L2 bandwidth: 26.15 -> 25.92 us without them)
+//   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared); the
+//     gated fixes are shared by the lanes of the warp (pv_correct_coop)
 //   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
 //   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
 // WITH_STEP = true is the WHOLE EKFLeeLanded control step in one launch (ozl_ekf_lee_landed_step): the ground vehicle that
@@ -85,8 +84,9 @@ struct StepIo {
 #endif
 template <int kEkfBlock, bool WITH_STEP>
 __global__ void OZL_EKF_BOUNDS(kEkfBlock)
-ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma, const HuskyArgs h, const StepIo io,
+ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma_arg, const HuskyArgs h, const StepIo io,
                      const int chain) {
+    const int use_tma = OZL_KEEP(64) ? use_tma_arg : 0;
     static_assert(kEkfBlock % 32 == 0, "whole warps");
     extern __shared__ __align__(128) float s_P[];            // [81][kEkfBlock] covariance tile, later the [kEkfBlock][13] observation tile
     __shared__ __align__(8) uint64_t s_bar;
@@ -116,7 +116,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     } else if (tid == 0) {
         s_step = atomicAdd(seq, 1ull);                                  // returned before this CTA's launch trigger
     }
-    // ---- stage-0 loads (registers) and L2 prefetches of everything the later stages will read
+    // ---- stage-0 loads (registers)
     bool rst = false;
     float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0;
     float wz0 = 0.f, pvl[3] = {0.f, 0.f, 0.f}, wp[3] = {0.f, 0.f, 0.f};
@@ -132,18 +132,6 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
     };
     if (valid) {
         if (!chained) stage0_loads();  // in flight while the block waits for its leader's read of the step record
-#pragma unroll
-        for (int k = 0; k < 4; ++k) prefetch_l2(a.ekf_q + (int64_t)k * a.n + i);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) prefetch_l2(a.ekf_P + (int64_t)k * a.n + i);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) prefetch_l2(a.pv_x + (int64_t)k * a.n + i);
-        if (WITH_STEP) {
-            prefetch_l2(plane2_ptr(pl, i));
-#pragma unroll
-            for (int k = 4; k < 7; ++k) prefetch_l2(plane4_ptr(pl, k, i));
-            prefetch_l2(io.progress + i);
-        }
     }
     __syncthreads();                   // the mbarrier is initialised, the step index is published
     if (chain_words) griddep_launch_dependents();   // after the tile's `started` word is final: the next launch's CTAs read it in launch order
@@ -157,7 +145,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         const uint32_t bytes = (uint32_t)n_here * 4u;
         if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
         for (int k = tid; k < 81; k += kEkfBlock) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
-    } else if (valid) {
+    } else if (valid && OZL_KEEP(64)) {
 #pragma unroll 9
         for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
     }
@@ -185,8 +173,9 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         // ---- attitude-EKF state: loads issued here (L2 hits), consumed after the sensor front-end
         EKF4 s;
         if (warm || rst) { s.q[0] = q[3]; s.q[1] = q[0]; s.q[2] = q[1]; s.q[3] = q[2]; }
-        else { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
-        for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = a.ekf_P[(int64_t)k * a.n + i];
+        else if (OZL_KEEP(128)) { for (int k = 0; k < 4; ++k) s.q[k] = a.ekf_q[(int64_t)k * a.n + i]; }
+        else { s.q[0] = 1.0; s.q[1] = s.q[2] = s.q[3] = 0.0; }
+        for (int k = 0; k < 16; ++k) s.P[k / 4][k % 4] = OZL_KEEP(128) ? a.ekf_P[(int64_t)k * a.n + i] : (k % 5 == 0 ? 1.0 : 0.0);
         // ---- sensor front-end (:345-346,366-375,397-406)
         FaultCfg f = a.f;
         f.step = step;
@@ -216,8 +205,8 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             const double gd[3] = {(double)gyr[0], (double)gyr[1], (double)gyr[2]};
             const double ad[4] = {(double)ang[3], (double)ang[0], (double)ang[1], (double)ang[2]};
             if (OZL_KEEP(2)) ekf_update(s, gd, ad, a.ekf_Dt, a.ekf_g_noise, 0.0000001);
-            for (int k = 0; k < 4; ++k) { a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
-            for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4];
+            for (int k = 0; k < 4; ++k) { if (OZL_KEEP(128)) a.ekf_q[(int64_t)k * a.n + i] = s.q[k]; q32[k] = (float)s.q[k]; }
+            if (OZL_KEEP(128)) { for (int k = 0; k < 16; ++k) a.ekf_P[(int64_t)k * a.n + i] = s.P[k / 4][k % 4]; }
         }
         // ---- PV filter (:353-358,397-444) on the shared-memory covariance tile
         {
@@ -243,7 +232,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
             for (int kk = 0; kk < 9; ++kk) a.pv_x[(int64_t)kk * a.n + i] = pvs.x[kk];
             for (int kk = 0; kk < 3; ++kk) { est_p[kk] = pvs.x[kk]; est_v[kk] = pvs.x[3 + kk]; }
         }
-        if (!use_tma) {
+        if (!use_tma && OZL_KEEP(64)) {
 #pragma unroll 9
             for (int k = 0; k < 81; ++k) a.pv_P[(int64_t)k * a.n + i] = s_P[k * kEkfBlock + tid];
         }
