@@ -5,7 +5,8 @@
 //     re-spawned in registers with the same draws ozl_step will make (reset_idx runs first, :312-314)
 //   * the step index, warm-up flag and the shared sensor-trigger counters come from the env's DEVICE step counter, so the
 //     whole task step (vehicle kernel, this kernel, step kernel) takes no host-changing argument: CUDA-graph capturable
-//   * HBM traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel)
+//   * traffic per env: root 72 B + EKF 2x160 B + PV 2x360 B + ~100 B of glue  (config 3: ~1.3 KB / env-step with the step kernel;
+//     L2-resident in steady state at 65536 envs)
 // (OZL_PHILOX_NOINLINE would keep ONE out-of-line copy of the counter RNG for the ~22 draw sites of this kernel: 20 KB less code,
 //  but measured slower on B200 -- 28.2 vs 27.1 us per 65536-env step -- so the draws stay inline)
 #include <cstdlib>
@@ -23,11 +24,13 @@
 #ifndef OZL_ABLATE
 #define OZL_ABLATE 0
 #endif
+// bits: 1 sensor faults, 2 EKF, 4 PV predict, 8 PV fixes, 16 Lee controller, 32 env step, 64 covariance tile in / out,
+//       128 EKF state loads / stores
 #define OZL_KEEP(bit) (!(OZL_ABLATE & (bit)))
 #ifndef OZL_PV_COOP
 #define OZL_PV_COOP 1       // warp-cooperative PV fixes (filters.cuh, pv_correct_coop); 0 = every thread runs its own fixes
 #endif
-constexpr int kEkfSmemRows = 81 + (OZL_PV_COOP ? 12 : 0);   // covariance tile (+ the cooperative fixes' scratch columns), floats per env   // 1 sensor faults, 2 EKF, 4 PV predict, 8 PV fixes, 16 Lee controller, 32 env step
+constexpr int kEkfSmemRows = 81 + (OZL_PV_COOP ? 12 : 0);   // covariance tile (+ the cooperative fixes' scratch columns), floats per env
 
 namespace ozl {
 

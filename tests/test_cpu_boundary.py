@@ -196,6 +196,15 @@ def test_c_abi_argument_errors_need_no_gpu(lib):
     bad.abi_version = 999
     h = ctypes.c_void_p()
     assert L.ozl_create(ctypes.byref(bad), 0, ctypes.byref(h)) != 0 and "abi_version" in msg()
+    # NVLink metrics exchange: rank / world validation and NULL handles
+    x = ctypes.c_void_p()
+    assert L.ozl_metrics_xchg_create(3, 2, 0, ctypes.byref(x)) != 0 and "rank 3 / world 2" in msg()
+    assert L.ozl_metrics_xchg_create(0, 99, 0, ctypes.byref(x)) != 0 and "world 99" in msg()
+    assert L.ozl_metrics_xchg_create(0, 1, 0, None) != 0 and "NULL argument" in msg()
+    assert L.ozl_metrics_push(None, None, None, None, 0, None) != 0 and "NULL env" in msg()
+    assert L.ozl_metrics_sum(None, None, None, None) != 0 and "NULL argument" in msg()
+    assert L.ozl_metrics_xchg_ipc_handle(None, None) != 0 and "NULL argument" in msg()
+    assert L.ozl_metrics_xchg_status(None, None, None, None, None) != 0 and "NULL exchange" in msg()
 
 
 def test_compat_shims_resolve_the_reference_trainer_imports(lib, tmp_path):

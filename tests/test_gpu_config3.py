@@ -119,15 +119,18 @@ def test_shared_trigger_counters_are_shard_invariant():
     assert torch.equal(full.pvfilters.get_states(), torch.cat([lo.pvfilters.get_states(), hi.pvfilters.get_states()]))
 
 
-@pytest.mark.parametrize("n", [65536, 4099, 300])
-def test_tile_chained_graph_replay_equals_eager_steps(n, monkeypatch):
+@pytest.mark.parametrize("n,force", [(65536, True), (4099, True), (300, True), (100000, False)])
+def test_tile_chained_graph_replay_equals_eager_steps(n, force, monkeypatch):
     """Steps captured back to back into one CUDA graph are launched TILE-CHAINED (csrc/tile_chain.cuh: launch L+1's CTA b waits only
     for launch L's CTA b, not for the whole grid, so consecutive launches overlap).  The replay must leave every buffer exactly as
     the same number of eager (classic, fully ordered) launches does: env planes, filter banks, glue buffers, surface tensors,
     episode statistics and the step counter -- over several replays, with eager steps in between (the first launch of every
     replay re-derives the tile sequence from the global step record)."""
     import ouzelum_b200
-    monkeypatch.setenv("OZL_EKF_CHAIN", "2")      # chain one-wave grids too (the default chains only grids longer than one wave)
+    if force:
+        monkeypatch.setenv("OZL_EKF_CHAIN", "2")  # chain one-wave grids too (the default chains only grids longer than one wave)
+    else:
+        monkeypatch.delenv("OZL_EKF_CHAIN", raising=False)     # 100000 envs = 1042 CTAs > 740 resident: chained by default
     mk = lambda: ouzelum_b200.make(
         seed=3, task="EKFLeeLanded", num_envs=n, sim_device=DEV, rl_device=DEV, headless=True,
         cfg=ouzelum_b200.task_config("EKFLeeLanded", n, seed=3, POMDP="random_noise", pomdp_prob=0.15, ConvergenceTime=5,
