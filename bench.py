@@ -278,8 +278,8 @@ def run_ours(args):
     # ---- headline: EXACTLY K steps, block-timed; every step's inputs are cold because (a) the steps rotate over S independent
     #      16384-env shards whose combined footprint (S x 4.9 MB) exceeds the 126 MB L2 and (b) the L2 is overwritten between the
     #      warm-up replay and the timed replay (K < S would otherwise re-touch warm shards).  The metrics vector is read every 16
-    #      steps inside the graph and, for N > 1, all-reduced with NCCL on a side stream inside the same graph (config 4's only
-    #      collective).  A ~0.4 ms GPU pre-roll sits in front of the first event so the host has enqueued every graph launch
+    #      steps inside the graph and, for N > 1, summed over the ranks inside the same graph (config 4's only collective: NVLink
+    #      peer-memory exchange issued by the metrics kernel, or an NCCL all-reduce on a side stream).  A ~0.4 ms GPU pre-roll sits in front of the first event so the host has enqueued every graph launch
     #      before the timed region begins: the event pair sees device time only, no host launch gaps.
     S = SHARDS
     shards = [(sim, obs, rew, reset, prog, tout, epr)]
@@ -301,16 +301,24 @@ def run_ours(args):
     if world > 1:
         collective = args.metrics_collective
         if collective == "peer":
+            from ouzelum_b200.dist import PeerMetrics
             try:
-                from ouzelum_b200.dist import PeerMetrics
-                peer = PeerMetrics(dev)
-            except Exception as e:  # noqa: BLE001 -- no cudaIpc between the ranks on this box: fall back to NCCL, and say so
-                sys.stderr.write(f"[bench] rank {rank}: peer-memory metrics exchange unavailable ({e!r}); using NCCL\n")
+                peer = PeerMetrics(dev, connect=False)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: metrics mailbox could not be created ({e!r})\n")
                 peer = None
             flag = torch.tensor([1 if peer is not None else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                peer, collective = None, "nccl"
+            if int(flag.item()) == 1:
+                try:
+                    peer._connect_ipc()                      # collective; raises on EVERY rank if any rank failed
+                except Exception as e:  # noqa: BLE001 -- no cudaIpc between the ranks on this box: fall back to NCCL, and say so
+                    sys.stderr.write(f"[bench] rank {rank}: peer-memory metrics exchange unavailable ({e!r}); using NCCL\n")
+                    peer = None
+            else:
+                peer = None
+            if peer is None:
+                collective = "nccl"
     nccl_in_graph = collective == "nccl"
     metrics_sum = torch.zeros(16, dtype=torch.float64, device=dev)
 

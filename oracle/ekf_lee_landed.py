@@ -63,7 +63,8 @@ class EKFLeeGlue:
         n, t = self.n, self.step
         warm = t < self.conv
         pos, quat, vel, angv = root[:, 0:3], root[:, 3:7], root[:, 7:10], root[:, 10:13]
-        acc = ((vel - self.prev_v) / self.dt).astype(f)
+        # `dv / self.dt` with dv a CUDA tensor and dt a Python float: torch-CUDA multiplies by the float32 reciprocal (BinaryDivTrueKernel.cu)
+        acc = ((vel - self.prev_v) * (f(1.0) / self.dt)).astype(f)
         acc[:, 2] = acc[:, 2] + f(9.8)
         mode = 0 if warm else self.mode
         gyr = _fault(angv, mode, self.prob, self.seed, self.ids, t, 1, False)

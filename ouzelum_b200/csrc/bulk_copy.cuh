@@ -46,6 +46,20 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
                  : "memory");
 }
 
+// TMA 2-D tiled copies through a tensor map (cp.async.bulk.tensor.2d; SASS UTMALDG / UTMASTG): one instruction moves a whole
+// [rows][cols] box between a row-strided global matrix and a dense shared-memory tile; columns beyond the matrix are zero-filled on
+// loads and clipped on stores.  `tmap` is the generic address of a `const __grid_constant__ CUtensorMap` kernel parameter.
+__device__ __forceinline__ void tma_load_2d(void* sdst, const void* tmap, int32_t x, int32_t y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(sdst)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int32_t x, int32_t y, const void* ssrc) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(smem_u32(ssrc))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 // Programmatic dependent launch (PDL).  A step kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
 // made resident while its predecessor on the stream is still draining; griddep_wait() blocks until the predecessor has
 // completed and its memory operations are visible (it returns at once when the launch carries no such dependency), and

@@ -183,7 +183,7 @@ struct FrontArgs {
     const float* root13;
     float* prev_linvel;      // [n,3] in/out
     float* sensors;          // [n,16] out
-    float dt;
+    float dt, inv_dt;        // inv_dt = 1.0f / dt: torch-CUDA evaluates `tensor / python_scalar` as a multiplication by the float32 reciprocal
     FaultCfg f;
     uint32_t env_id_base;
 };
@@ -194,7 +194,7 @@ __global__ void sensor_frontend_kernel(const FrontArgs a) {
     const uint32_t genv = a.env_id_base + (uint32_t)i;
     float acc[3], gyr[3], ang[4], pos[3], vel[3];
     for (int j = 0; j < 3; ++j) {
-        acc[j] = (r[7 + j] - a.prev_linvel[i * 3 + j]) / a.dt;           // :345-346
+        acc[j] = (r[7 + j] - a.prev_linvel[i * 3 + j]) * a.inv_dt;       // :345-346 (dv / dt on a CUDA tensor)
         gyr[j] = r[10 + j]; pos[j] = r[j]; vel[j] = r[7 + j];
     }
     acc[2] = acc[2] + 9.8f;                                              // :367
@@ -354,7 +354,7 @@ extern "C" int ozl_sensor_frontend(int64_t n, const float* root13, float* prev_l
     if (!root13 || !prev_linvel3 || !sensors16) return set_error("ozl_sensor_frontend: NULL buffer");
     if (mode < 0 || mode > 3) return set_error("pomdp was not in ['flicker', 'random_noise', 'flickering_and_random_noise']!");
     FrontArgs a;
-    a.n = n; a.root13 = root13; a.prev_linvel = prev_linvel3; a.sensors = sensors16; a.dt = dt; a.f.mode = mode;
+    a.n = n; a.root13 = root13; a.prev_linvel = prev_linvel3; a.sensors = sensors16; a.dt = dt; a.inv_dt = 1.0f / dt; a.f.mode = mode;
     a.f.flicker_p = (mode == 3) ? 0.1f : pomdp_prob;
     const float lo = (float)(1.0 - (double)pomdp_prob), hi = (float)(1.0 + (double)pomdp_prob);
     a.f.noise_lo = lo; a.f.noise_range = hi - lo;

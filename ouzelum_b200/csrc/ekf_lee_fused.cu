@@ -10,6 +10,7 @@
 // (OZL_PHILOX_NOINLINE would keep ONE out-of-line copy of the counter RNG for the ~22 draw sites of this kernel: 20 KB less code,
 //  but measured slower on B200 -- 28.2 vs 27.1 us per 65536-env step -- so the draws stay inline)
 #include <cstdlib>
+#include <cuda.h>              // CUtensorMap (types only: the encoder is looked up through cudaGetDriverEntryPoint, no libcuda link)
 #include "internal.h"
 #include "bulk_copy.cuh"
 #include "quad_io.cuh"
@@ -44,7 +45,7 @@ struct EkfLeeArgs {
     const int64_t* reset;                 // [n]
     float4* wrench;                       // [n] out
     float* est13;   float4* cmd4;         // optional debug outputs
-    float dt, dt2, mg, hover;
+    float dt, dt2, inv_dt, mg, hover;
     int64_t convergence;
     FaultCfg f;                           // mode / probabilities / seed (step filled in-kernel)
     uint32_t pos_period, pos_phase, vel_period, vel_phase;
@@ -88,7 +89,7 @@ struct StepIo {
 template <int kEkfBlock, bool WITH_STEP>
 __global__ void OZL_EKF_BOUNDS(kEkfBlock)
 ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma_arg, const HuskyArgs h, const StepIo io,
-                     const int chain) {
+                     const int chain, const __grid_constant__ CUtensorMap tmap) {
     const int use_tma = OZL_KEEP(64) ? use_tma_arg : 0;
     static_assert(kEkfBlock % 32 == 0, "whole warps");
     extern __shared__ __align__(128) float s_P[];            // [81][kEkfBlock] covariance tile, later the [kEkfBlock][13] observation tile
@@ -144,7 +145,13 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         if (valid) stage0_loads();
         fence_proxy_async_all();       // the bulk loads below (async proxy) are ordered behind the acquire
     }
-    if (use_tma) {
+    if (use_tma == 2) {
+        // ONE 2-D tensor-map copy brings the whole [81][kEkfBlock] box in (columns beyond N are zero-filled and still counted)
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, 81u * (uint32_t)kEkfBlock * 4u);
+            tma_load_2d(s_P, &tmap, (int32_t)base, 0, &s_bar);
+        }
+    } else if (use_tma) {
         const uint32_t bytes = (uint32_t)n_here * 4u;
         if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
         for (int k = tid; k < 81; k += kEkfBlock) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
@@ -185,7 +192,7 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         if (warm) f.mode = 0;
         float acc[3], gyr[3], ang[4], pos[3], vel[3];
         for (int j = 0; j < 3; ++j) {
-            acc[j] = (v[j] - pvl[j]) / a.dt;
+            acc[j] = (v[j] - pvl[j]) * a.inv_dt;     // :345-346: `dv / dt` on a CUDA tensor = multiplication by the float32 reciprocal
             gyr[j] = w[j]; pos[j] = p[j]; vel[j] = v[j];
             a.prev_linvel[i * 3 + j] = v[j];                                              // :454
         }
@@ -258,7 +265,8 @@ ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const 
         // drain: every thread's filter writes are made visible to the async proxy, then 81 threads issue one plane store each
         fence_proxy_async_smem();
         __syncthreads();
-        for (int k = tid; k < 81; k += kEkfBlock) bulk_store_s2g(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, (uint32_t)n_here * 4u);
+        if (use_tma == 2) { if (tid == 0) tma_store_2d(&tmap, (int32_t)base, 0, s_P); }
+        else for (int k = tid; k < 81; k += kEkfBlock) bulk_store_s2g(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, (uint32_t)n_here * 4u);
     }
     // the env's remaining planes for the step below: loads issued before the controller arithmetic (L2 hits by now)
     Loaded L;
@@ -347,6 +355,41 @@ static int ozl_ekf_lee_block(const ozl_env* env, int64_t n) {
     return 96;
 }
 
+// 2-D tensor map over the caller's [81][N] covariance planes, box = [81][block] (cached in the handle: the pointer is fixed per task).
+// Returns 0 when env->pv_tmap is valid for (P, block).
+static int ozl_encode_pv_tmap(ozl_env* env, const float* P, int64_t n, int block) {
+    if (env->pv_tmap_ptr == P && env->pv_tmap_block == block) return 0;
+    if (block > 256 || n < block) return 1;                       // box dimensions are limited to 256 elements
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return 1;
+    const cuuint64_t gdim[2] = {(cuuint64_t)n, 81ull};
+    const cuuint64_t gstr[1] = {(cuuint64_t)n * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)block, 81u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (fn(reinterpret_cast<CUtensorMap*>(env->pv_tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P), gdim, gstr, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        env->pv_tmap_ptr = nullptr;
+        return 1;
+    }
+    env->pv_tmap_ptr = P;
+    env->pv_tmap_block = block;
+    return 0;
+}
+
 static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_husky_args* husky, const StepIo io, void* stream) {
     if (!env || !in) return set_error("ozl_ekf_lee_step: NULL argument");
     if (!in->ekf_q4xN || !in->ekf_P16xN || !in->pv_x9xN || !in->pv_P81xN || !in->prev_linvel3 || !in->waypoint3 || !in->target3 ||
@@ -360,7 +403,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     a.ekf_q = in->ekf_q4xN; a.ekf_P = in->ekf_P16xN; a.pv_x = in->pv_x9xN; a.pv_P = in->pv_P81xN;
     a.prev_linvel = in->prev_linvel3; a.waypoint = in->waypoint3; a.target = in->target3; a.reset = in->reset;
     a.wrench = (float4*)in->wrench4; a.est13 = in->est13; a.cmd4 = (float4*)in->cmd4;
-    a.dt = in->dt; a.dt2 = (float)((double)in->dt * (double)in->dt); a.mg = in->mg; a.hover = in->hover_force;
+    a.dt = in->dt; a.dt2 = (float)((double)in->dt * (double)in->dt); a.inv_dt = 1.0f / in->dt; a.mg = in->mg; a.hover = in->hover_force;
     a.convergence = in->convergence_steps;
     a.f.mode = in->pomdp_mode;
     a.f.flicker_p = (in->pomdp_mode == 3) ? 0.1f : in->pomdp_prob;
@@ -374,7 +417,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     for (int k = 0; k < 3; ++k) { a.g.kP[k] = in->gains16[k]; a.g.kV[k] = in->gains16[3 + k]; a.g.kR[k] = in->gains16[6 + k]; a.g.kO[k] = in->gains16[9 + k]; }
     for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
     // TMA path: every [k][N] plane slice of a block must start on a 16-byte boundary and be a multiple of 16 bytes long
-    const int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);
+    int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);       // 1: 81 plane copies (1-D), 2: one tensor-map copy
     HuskyArgs h{};
     if (husky) {
         if (ozl_fill_husky_args(husky, h, "ozl_ekf_lee_landed_step")) return 1;
@@ -392,6 +435,11 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     const int block = ozl_ekf_lee_block(env, a.n);
     const unsigned grid = (unsigned)((a.n + block - 1) / block);
     const size_t smem = (size_t)kEkfSmemRows * block * sizeof(float);
+    {
+        static int tmap_mode = -1;                                  // OZL_EKF_TMAP=0: keep the 81 plane copies
+        if (tmap_mode < 0) { const char* v = getenv("OZL_EKF_TMAP"); tmap_mode = v ? atoi(v) : 1; }
+        if (use_tma && tmap_mode && ozl_encode_pv_tmap(env, a.pv_P, a.n, block) == 0) use_tma = 2;
+    }
     const long long slots = (long long)env->sm_count * ekf_minb(block);
     const bool may_chain = husky && env->use_pdl && (env->chain_mode == 2 || (env->chain_mode == 1 && (long long)grid > slots));
     int chain = may_chain ? 0 : -1;
@@ -415,7 +463,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
             attr_set = true;                                                                                                    \
         }                                                                                                                       \
         rc = launch_pdl_smem(env, ekf_lee_fused_kernel<B, WS>, dim3(grid), dim3(B), smem, (cudaStream_t)stream, env->dev,       \
-                             env->pl, a, use_tma, h, io, chain);                                                                \
+                             env->pl, a, use_tma, h, io, chain, *reinterpret_cast<const CUtensorMap*>(env->pv_tmap));          \
     } while (0)
     if (husky) {
         if (block == 512) OZL_LAUNCH_EKF(512, true); else if (block == 256) OZL_LAUNCH_EKF(256, true);

@@ -74,6 +74,10 @@ struct ozl_env {
     unsigned int host_seq;              // sequence number of the last host step launched
     int use_host_flag;                  // OZL_HOST_FLAG=0 turns the completion word off (stream synchronise instead)
     // tile-chained step launches (tile_chain.cuh): the graph node of the last chained launch captured on this handle
+    // 2-D tensor map of the caller's [81][N] PV covariance planes with a [81][block] box (ekf_lee_fused.cu), cached per (pointer, block)
+    alignas(64) unsigned char pv_tmap[128];
+    const void* pv_tmap_ptr;
+    int pv_tmap_block;
     int chain_mode;                     // OZL_EKF_CHAIN: 0 = never chain, 1 = chain launches that are provably adjacent in a stream capture
     unsigned long long chain_capture_id;
     void* chain_last_node;

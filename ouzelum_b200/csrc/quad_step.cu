@@ -754,6 +754,8 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
         e->chain_mode = cv ? atoi(cv) : 1;
         e->chain_capture_id = 0;
         e->chain_last_node = nullptr;
+        e->pv_tmap_ptr = nullptr;
+        e->pv_tmap_block = 0;
     }
     {
         const char* hv = getenv("OZL_HOST_FLAG");

@@ -119,15 +119,26 @@ class PeerMetrics:
             self._connect_ipc()
 
     def _connect_ipc(self):
+        """Collective: every rank of the process group must call it.  Either every rank ends up connected or every rank raises (a
+        rank that fails to map a peer's mailbox still takes part in the collectives below, so nobody is left waiting)."""
         import ctypes as C
-        from ._lib import check, lib
+        from ._lib import lib, last_error
         mine = (C.c_ubyte * 64)()
-        check(lib.ozl_metrics_xchg_ipc_handle(self._h, mine))
+        ok, why = True, ""
+        if lib.ozl_metrics_xchg_ipc_handle(self._h, mine) != 0:
+            ok, why = False, last_error()
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, bytes(mine))          # host-side, once: plumbing
-        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(gathered))
-        check(lib.ozl_metrics_xchg_connect_ipc(self._h, blob))
-        dist.barrier()                                         # every mailbox is mapped before anyone pushes
+        dist.all_gather_object(gathered, bytes(mine) if ok else None)          # host-side, once: plumbing
+        if ok and all(g is not None for g in gathered):
+            blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(gathered))
+            if lib.ozl_metrics_xchg_connect_ipc(self._h, blob) != 0:
+                ok, why = False, last_error()
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)            # also the barrier: every mailbox is mapped before anyone pushes
+        if int(flag.item()) == 0:
+            raise RuntimeError(f"ouzelum_b200: NVLink metrics exchange could not be connected on every rank ({why or 'a peer failed'})")
 
     @staticmethod
     def connect_same_process(exchanges):
