@@ -88,7 +88,7 @@ struct StepIo {
 #endif
 template <int kEkfBlock, bool WITH_STEP>
 __global__ void OZL_EKF_BOUNDS(kEkfBlock)
-ekf_lee_fused_kernel(const DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma_arg, const HuskyArgs h, const StepIo io,
+ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const EkfLeeArgs a, const int use_tma_arg, const HuskyArgs h, const StepIo io,
                      const int chain, const __grid_constant__ CUtensorMap tmap) {
     const int use_tma = OZL_KEEP(64) ? use_tma_arg : 0;
     static_assert(kEkfBlock % 32 == 0, "whole warps");

@@ -212,16 +212,29 @@ __device__ __forceinline__ void pv_correct_coop(PVShared<STRIDE>& s, float* scr_
     const unsigned busy = __ballot_sync(wmask, job >= 0);
     if (busy == 0u) return;                                  // uniform
     const int njobs = __popc(busy), nl = __popc(wmask);
-    int S = nl / njobs;
+    // S = nl / njobs and jidx = wrank / S for operands <= 32: one MUFU reciprocal each (the +0.5 keeps exact multiples on the right
+    // side of the floor; an integer division here compiles to a call into a helper at the far end of a 128 KB kernel image)
+    int S = (int)__fdividef((float)nl + 0.5f, (float)njobs);
     S = S > 9 ? 9 : S;
     if (job >= 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) scr_col[k * STRIDE] = z[k] - (job ? s.x[3 + k] : s.x[k]);
     }
     const int wrank = __popc(wmask & ((1u << lane) - 1u));
-    const int jidx = wrank / S, sub = wrank - jidx * S;
+    const int jidx = (int)__fdividef((float)wrank + 0.5f, (float)S), sub = wrank - jidx * S;
     const bool working = jidx < njobs;
-    const int owner = working ? (int)__fns(busy, 0, jidx + 1) : lane;
+    // lane of the jidx-th fixing env: position of the (jidx + 1)-th set bit of `busy`, by a 5-step binary search on popcounts
+    int owner = lane;
+    if (working) {
+        unsigned m = busy;
+        int n = jidx, pos = 0, t;
+        t = __popc(m & 0xFFFFu); if (n >= t) { pos += 16; n -= t; m >>= 16; }
+        t = __popc(m & 0xFFu);   if (n >= t) { pos += 8;  n -= t; m >>= 8; }
+        t = __popc(m & 0xFu);    if (n >= t) { pos += 4;  n -= t; m >>= 4; }
+        t = __popc(m & 0x3u);    if (n >= t) { pos += 2;  n -= t; m >>= 2; }
+        t = (int)(m & 1u);       if (n >= t) { pos += 1; }
+        owner = pos;
+    }
     const int LO = __shfl_sync(wmask, job, owner);
     __syncwarp(wmask);                                       // innovations are published
     float* const Pc = s.P + (owner - lane);                  // the owner's column of the covariance tile

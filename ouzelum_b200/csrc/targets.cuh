@@ -65,24 +65,28 @@ __device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, ui
     tgt = lookup(a, id.x, id.y, p.w);
     // differential_drive(pos, target, heading, (3.0, 1000))  (controllers.py:15-43)
     dx = tgt.x - p.x; dy = tgt.y - p.y;
-    float dth = map_to_pi(atan2f(dy, dx) - map_to_pi(p.z));
+    // atan2f(+0, dx) = 0 or pi; taken out of the library call because its internal division sees the zero numerator (see
+    // div_rn_normal) whenever a vehicle drives along a line of constant y
+    float bearing = dx < 0.0f ? kPi : 0.0f;
+    if (dy != 0.0f) bearing = atan2f(dy, dx);
+    float dth = map_to_pi(bearing - map_to_pi(p.z));
     if (dth < a.ang_thresh && dth > -a.ang_thresh) dth = 0.0f;
     const float lin = sqrtf(dx * dx + dy * dy) * a.kp_lin;
     const float ang = dth * a.kp_ang;
-    float left = (2.0f * lin + ang * kWheelBase) / (2.0f * kWheelRadius);
-    float right = (2.0f * lin - ang * kWheelBase) / (2.0f * kWheelRadius);
+    float left = div_rn_normal(2.0f * lin + ang * kWheelBase, 2.0f * kWheelRadius);
+    float right = div_rn_normal(2.0f * lin - ang * kWheelBase, 2.0f * kWheelRadius);
     const float mx = fmaxf(fabsf(left), fabsf(right));
     if (mx > kMaxWheel) { const float sc = kMaxWheel / mx; left *= sc; right *= sc; }
     if (a.wheels) reinterpret_cast<float4*>(a.wheels)[i] = make_float4(right, left, right, left);
     // kinematic unicycle in place of the PhysX vehicle
     const float v = kWheelRadius * (right + left) * 0.5f;
-    const float wz = kWheelRadius * (left - right) / kWheelBase;
+    const float wz = div_rn_normal(kWheelRadius * (left - right), kWheelBase);
     float sh, ch;
     sincosf(p.z, &sh, &ch);
     p.x = p.x + ch * (v * a.dt);
     p.y = p.y + sh * (v * a.dt);
     float h = p.z + wz * a.dt;
-    h = h - (2.0f * kPi) * floorf(h / (2.0f * kPi));                          // heading in [0, 2 pi) like get_euler_xyz
+    h = h - (2.0f * kPi) * floorf(div_rn_normal(h, 2.0f * kPi));                          // heading in [0, 2 pi) like get_euler_xyz
     p.z = h;
     a.pose[i] = p;
     a.idx[i] = id;
