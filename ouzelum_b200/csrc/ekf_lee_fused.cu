@@ -156,7 +156,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
         for (int k = tid; k < 81; k += kEkfBlock) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
     } else if (valid && OZL_KEEP(64)) {
-#pragma unroll 9
+#pragma unroll 3          // fallback path (N % 4 != 0): kept small, this kernel is instruction-fetch bound
         for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
     }
     const uint64_t step = s_step;
@@ -170,7 +170,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         // ---- true root state (post reset_idx)
         float p[3], v[3];
         if (rst) {
-            const uint4 r = draw(c.seed, genv, step, P_SPAWN);
+            const uint4 r = draw_cold(c.seed, genv, step, P_SPAWN);
             p[0] = c.spawn_base[0] + (c.spawn_range[0] * u01(r.x) + c.spawn_lo[0]);
             p[1] = c.spawn_base[1] + (c.spawn_range[1] * u01(r.y) + c.spawn_lo[1]);
             p[2] = c.spawn_base[2] + (c.spawn_range[2] * u01(r.z) + c.spawn_lo[2]);
@@ -243,7 +243,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
             for (int kk = 0; kk < 3; ++kk) { est_p[kk] = pvs.x[kk]; est_v[kk] = pvs.x[3 + kk]; }
         }
         if (!use_tma && OZL_KEEP(64)) {
-#pragma unroll 9
+#pragma unroll 3
             for (int k = 0; k < 81; ++k) a.pv_P[(int64_t)k * a.n + i] = s_P[k * kEkfBlock + tid];
         }
         // (the TMA drain of the tile is issued below, after the block barrier, and overlaps the controller)
@@ -321,6 +321,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         if ((nflt & 3) == 0) {
             if (tid == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
         } else {
+#pragma unroll 1
             for (int k = tid; k < nflt; k += kEkfBlock) dst[k] = s_obs[k];
         }
     }

@@ -48,6 +48,19 @@ __device__ __forceinline__ uint4 draw(uint64_t seed, uint32_t env, uint64_t step
                          (uint32_t)(seed >> 32));
 }
 
+// Draws on rarely taken paths (episode reset: spawn, rotor fault, domain randomisation, target / trajectory re-draws).  A TU whose
+// kernel is instruction-fetch bound defines OZL_COLD_DRAW_NOINLINE and these sites share ONE out-of-line copy of the ten rounds
+// (~90 instructions each otherwise); the per-step draws stay inline everywhere.  Same function, same bits.
+#ifdef OZL_COLD_DRAW_NOINLINE
+static __device__ __noinline__ uint4 draw_cold(uint64_t seed, uint32_t env, uint64_t step, uint32_t purpose) {
+    return draw(seed, env, step, purpose);
+}
+#else
+__device__ __forceinline__ uint4 draw_cold(uint64_t seed, uint32_t env, uint64_t step, uint32_t purpose) {
+    return draw(seed, env, step, purpose);
+}
+#endif
+
 // uint32 -> [0,1): top 24 bits * 2^-24, exact in float32
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 

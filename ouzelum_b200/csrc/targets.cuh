@@ -36,7 +36,7 @@ __device__ __forceinline__ float2 lookup(const HuskyArgs& a, int traj, int index
     return make_float2(w.x * s, w.y * s);
 }
 __device__ __forceinline__ void redraw(const HuskyArgs& a, uint32_t genv, uint64_t step, int& traj, float& s) {
-    const uint4 r = draw(a.seed, genv, step, P_HUSKY);
+    const uint4 r = draw_cold(a.seed, genv, step, P_HUSKY);
     traj = (int)__umulhi(r.x, 3u);                                           // torch.randint(0, 3)      landing.py:210/240
     const float scale = __fadd_rn(0.8f, __fmul_rn(0.4f, u01(r.y)));                              // rand*(1.2-0.8)+0.8       landing.py:211/241
     s = scale * ((r.z & 1u) ? 1.0f : -1.0f);                                 // randint(0,2)*2-1         landing.py:212/242
@@ -49,7 +49,7 @@ __device__ __forceinline__ void husky_step_env(const HuskyArgs& a, int64_t i, ui
     const uint32_t genv = a.env_id_base + (uint32_t)i;
     // re-spawn a strayed vehicle when its drone resets (landing.py:263-270)
     if (a.reset && a.reset[i] != 0 && (fabsf(p.x) > a.respawn_limit || fabsf(p.y) > a.respawn_limit)) {
-        const uint4 r = draw(a.seed, genv, step, P_HUSKY + 1);
+        const uint4 r = draw_cold(a.seed, genv, step, P_HUSKY + 1);
         p.x = __fadd_rn(__fmul_rn(3.0f, u01(r.x)), -1.5f);
         p.y = __fadd_rn(__fmul_rn(3.0f, u01(r.y)), -1.5f);
         p.z = 0.0f;
