@@ -32,6 +32,7 @@
 #define OZL_PV_COOP 1       // warp-cooperative PV fixes (filters.cuh, pv_correct_coop); 0 = every thread runs its own fixes
 #endif
 constexpr int kEkfSmemRows = 81 + (OZL_PV_COOP ? 12 : 0);   // covariance tile (+ the cooperative fixes' scratch columns), floats per env
+constexpr int kWarpTile = kEkfSmemRows * 32;                // floats of shared memory per WARP: [81][32] tile (+ [12][32] scratch)
 
 namespace ozl {
 
@@ -61,22 +62,25 @@ struct EkfLeeArgs {
 // with 16; 96-env CTAs spread the same envs as 4 or 5 CTAs (12 or 15 warps).  See ozl_ekf_lee_block().
 constexpr int ekf_minb(int block) { return block <= 64 ? 8 : (block <= 96 ? 5 : (block <= 128 ? 4 : (block <= 256 ? 2 : 1))); }
 
-// Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA):
-//   * the block's [81][kEkfBlock] slice of the PV covariance planes is brought into SHARED memory by 81 TMA bulk copies
-//     (one plane each, issued by different threads, completing on one mbarrier) before anything else: the 31 KB of loads fly
-//     while every thread runs the vehicle, the sensor front-end and the float64 attitude EKF out of registers
+// Layout of the work inside a CTA (one env per thread, kEkfBlock envs per CTA, shared memory WARP-PRIVATE):
+//   * each warp's [81][32] slice of the PV covariance planes is brought into its own shared-memory tile by ONE 2-D tensor-map copy
+//     (cp.async.bulk.tensor.2d on the warp's mbarrier; the caller's [81][N] planes are described by a CUtensorMap with an [81][32]
+//     box) before anything else: the loads fly while every thread runs the vehicle, the sensor front-end and the float64 attitude
+//     EKF out of registers.  (81 separate 1-D bulk copies per CTA compiled to an elect / broadcast loop per warp: 24.95 -> 23.9 us)
 //   * each stage's loads are issued before the previous stage's arithmetic.  (Round 2 also prefetched everything the later stages
 //     read into L2 at the top; with the state L2-resident in steady state -- profiles/r02q_steady_state_dram_traffic.json -- the
 //     ~40 prefetch instructions per thread only cost L2 bandwidth: 26.15 -> 25.92 us without them)
-//   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared); the
+//   * the PV filter then works in place on the thread's column of that tile with rolled loops (filters.cuh, PVShared<32>); the
 //     gated fixes are shared by the lanes of the warp (pv_correct_coop)
-//   * the updated tile leaves through 81 TMA bulk stores while the threads run the waypoint logic and the Lee controller
-//   * N % 4 != 0 (plane slices not 16-byte aligned): the same tile is filled / drained with plain coalesced loads / stores
+//   * the updated tile leaves through one tensor-map store per warp while the threads run the waypoint logic and the Lee controller
+//   * after the step-index broadcast nothing needs a block barrier (measured equal to the block-wide tile: 23.7 vs 23.6 us; kept
+//     because the box no longer depends on the CTA size)
+//   * N % 4 != 0 (plane rows not 16-byte aligned) or no tensor map: the same tile is filled / drained with plain coalesced loads / stores
 // WITH_STEP = true is the WHOLE EKFLeeLanded control step in one launch (ozl_ekf_lee_landed_step): the ground vehicle that
 // carries the target runs first (targets.cuh), and after the controller the same thread applies its wrench to its env --
 // env_step(ACT_WRENCH) with the vehicle's target, sensor-fault epilogue on the observation, stores, episode statistics and
-// the step-counter retirement of quad_step_kernel (quad_io.cuh).  The observation tile reuses the covariance tile's shared
-// memory once the bulk drain has read it.  Replaces three launches (husky_step, ekf_lee_fused, quad_step) and their re-reads.
+// the step-counter retirement of quad_step_kernel (quad_io.cuh).  Each warp stages its [32][13] observation rows in its covariance
+// tile once the drain has read it.  Replaces three launches (husky_step, ekf_lee_fused, quad_step) and their re-reads.
 struct StepIo {
     float* obs; float* rew; int64_t* reset; int64_t* progress; uint8_t* timeout; float* ep_ret;
 };
@@ -92,10 +96,16 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
                      const int chain, const __grid_constant__ CUtensorMap tmap) {
     const int use_tma = OZL_KEEP(64) ? use_tma_arg : 0;
     static_assert(kEkfBlock % 32 == 0, "whole warps");
-    extern __shared__ __align__(128) float s_P[];            // [81][kEkfBlock] covariance tile, later the [kEkfBlock][13] observation tile
-    __shared__ __align__(8) uint64_t s_bar;
+    // Shared memory is WARP-PRIVATE: warp w owns [81][32] floats of covariance tile (+ [12][32] of scratch for the cooperative
+    // fixes), its own mbarrier, and later stages its [32][13] observation rows in the same tile.  Nothing after the step-index
+    // broadcast needs a block barrier: the tile comes and goes through per-warp tensor-map copies, the fixes are intra-warp.
+    extern __shared__ __align__(128) float s_all[];
+    __shared__ __align__(8) uint64_t s_bars[kEkfBlock / 32];
     __shared__ uint64_t s_step;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    float* const s_P = s_all + warp * kWarpTile;             // this warp's tile, element (k, lane) at s_P[k * 32 + lane]
+    uint64_t* const s_bar = &s_bars[warp];
     const int64_t base = (int64_t)blockIdx.x * kEkfBlock;
     const int64_t i = base + tid;
     const bool valid = i < a.n;
@@ -103,7 +113,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
     // valid lanes of this warp (a prefix): the participants of the warp-cooperative PV fixes
     const int wl = n_here - (tid & ~31);
     const unsigned wmask = wl >= 32 ? 0xffffffffu : (wl > 0 ? (1u << wl) - 1u : 0u);
-    if (tid == 0 && use_tma) mbar_init(&s_bar, 1);
+    if (lane == 0 && use_tma) mbar_init(s_bar, 1);
     // tile-chained launches (tile_chain.cuh): chained == this launch does NOT wait for the previous grid, only for its own tile
     // chain: -1 classic launch (no tile words touched), 0 first launch of a chain, 1 chained
     const bool chained = WITH_STEP && chain > 0;
@@ -145,19 +155,16 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         if (valid) stage0_loads();
         fence_proxy_async_all();       // the bulk loads below (async proxy) are ordered behind the acquire
     }
-    if (use_tma == 2) {
-        // ONE 2-D tensor-map copy brings the whole [81][kEkfBlock] box in (columns beyond N are zero-filled and still counted)
-        if (tid == 0) {
-            mbar_expect_tx(&s_bar, 81u * (uint32_t)kEkfBlock * 4u);
-            tma_load_2d(s_P, &tmap, (int32_t)base, 0, &s_bar);
+    const int64_t wbase = base + warp * 32;                  // first env of this warp
+    if (use_tma) {
+        // ONE 2-D tensor-map copy per warp brings its [81][32] box in (columns beyond N are zero-filled and still counted)
+        if (lane == 0 && wbase < a.n) {
+            mbar_expect_tx(s_bar, 81u * 32u * 4u);
+            tma_load_2d(s_P, &tmap, (int32_t)wbase, 0, s_bar);
         }
-    } else if (use_tma) {
-        const uint32_t bytes = (uint32_t)n_here * 4u;
-        if (tid == 0) mbar_expect_tx(&s_bar, 81u * bytes);
-        for (int k = tid; k < 81; k += kEkfBlock) bulk_load_g2s(s_P + k * kEkfBlock, a.pv_P + (int64_t)k * a.n + base, bytes, &s_bar);
     } else if (valid && OZL_KEEP(64)) {
-#pragma unroll 3          // fallback path (N % 4 != 0): kept small, this kernel is instruction-fetch bound
-        for (int k = 0; k < 81; ++k) s_P[k * kEkfBlock + tid] = a.pv_P[(int64_t)k * a.n + i];
+#pragma unroll 3          // fallback path (N % 4 != 0 or no tensor map): kept small, this kernel is instruction-fetch bound
+        for (int k = 0; k < 81; ++k) s_P[k * 32 + lane] = a.pv_P[(int64_t)k * a.n + i];
     }
     const uint64_t step = s_step;
     const bool warm = (int64_t)step < a.convergence;                                     // :339
@@ -206,8 +213,8 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
             sensor_fault(f, genv, 6, false, vel, 3);
         }
         // ---- PV state: loads issued before the EKF arithmetic, consumed after it
-        PVShared<kEkfBlock> pvs;
-        pvs.P = s_P + tid;
+        PVShared<32> pvs;
+        pvs.P = s_P + lane;
         for (int k = 0; k < 9; ++k) pvs.x[k] = a.pv_x[(int64_t)k * a.n + i];
         // ---- attitude EKF (:348-352,378-391), float64 in registers
         float q32[4];
@@ -222,7 +229,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         {
             if (rst) { for (int k = 0; k < 3; ++k) { pvs.x[k] = p[k]; pvs.x[3 + k] = v[k]; pvs.x[6 + k] = 0.f; } }
             const float qt[4] = {q[3], q[0], q[1], q[2]};
-            if (use_tma) mbar_wait(&s_bar, 0);                    // the covariance tile has landed
+            if (use_tma) mbar_wait(s_bar, 0);                    // the covariance tile has landed
             if (OZL_KEEP(4)) pv_predict(pvs, acc, warm ? qt : q32, a.dt, a.dt2, a.acc_var);
             // shared sensor-trigger counters (:425-440): the reference advances them once per env-iteration, i.e. the k-th
             // iteration overall is step * N_total + GLOBAL env id (invariant to how the envs are sharded over GPUs)
@@ -232,9 +239,9 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
             const float zero3[3] = {0.f, 0.f, 0.f};                                                  // gps_var=None => R = 0
 #if OZL_PV_COOP
             // warp-cooperative fixes (filters.cuh): first fix of every env, then the velocity fix of the envs that had both
-            float* const scr = s_P + 81 * kEkfBlock + tid;
-            pv_correct_coop(pvs, scr, wmask, tid & 31, fix_pos ? 0 : (fix_vel ? 3 : -1), fix_pos ? pos : vel, a.pos_var, zero3);
-            pv_correct_coop(pvs, scr, wmask, tid & 31, (fix_pos && fix_vel) ? 3 : -1, vel, a.pos_var, zero3);
+            float* const scr = s_P + 81 * 32 + lane;
+            pv_correct_coop(pvs, scr, wmask, lane, fix_pos ? 0 : (fix_vel ? 3 : -1), fix_pos ? pos : vel, a.pos_var, zero3);
+            pv_correct_coop(pvs, scr, wmask, lane, (fix_pos && fix_vel) ? 3 : -1, vel, a.pos_var, zero3);
 #else
             if (fix_pos) pv_correct<0>(pvs, pos, a.pos_var);
             if (fix_vel) pv_correct<3>(pvs, vel, zero3);
@@ -244,7 +251,7 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         }
         if (!use_tma && OZL_KEEP(64)) {
 #pragma unroll 3
-            for (int k = 0; k < 81; ++k) a.pv_P[(int64_t)k * a.n + i] = s_P[k * kEkfBlock + tid];
+            for (int k = 0; k < 81; ++k) a.pv_P[(int64_t)k * a.n + i] = s_P[k * 32 + lane];
         }
         // (the TMA drain of the tile is issued below, after the block barrier, and overlaps the controller)
         // ---- waypoint + controller (:458-529)
@@ -262,11 +269,10 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         cmd[0] = wp[0] * a.g.scale[0]; cmd[1] = wp[1] * a.g.scale[1]; cmd[2] = wp[2] * a.g.scale[2]; cmd[3] = 0.0f;
     }
     if (use_tma) {
-        // drain: every thread's filter writes are made visible to the async proxy, then 81 threads issue one plane store each
+        // drain: the warp's filter writes are made visible to the async proxy, then its leader issues one tensor-map store
         fence_proxy_async_smem();
-        __syncthreads();
-        if (use_tma == 2) { if (tid == 0) tma_store_2d(&tmap, (int32_t)base, 0, s_P); }
-        else for (int k = tid; k < 81; k += kEkfBlock) bulk_store_s2g(a.pv_P + (int64_t)k * a.n + base, s_P + k * kEkfBlock, (uint32_t)n_here * 4u);
+        __syncwarp();
+        if (lane == 0 && wbase < a.n) tma_store_2d(&tmap, (int32_t)wbase, 0, s_P);
     }
     // the env's remaining planes for the step below: loads issued before the controller arithmetic (L2 hits by now)
     Loaded L;
@@ -286,15 +292,15 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         }
         a.wrench[i] = wr;
     }
-    if (use_tma && tid < 81) bulk_wait_read_all();      // the tile must stay alive until the bulk stores have read it
+    if (use_tma && lane == 0) bulk_wait_read_all();     // the tile must stay alive until the bulk store has read it
     if (!WITH_STEP) return;
 
     // ---- the env step itself (quad_step_kernel's body, wrench actuation, target from the vehicle)
     StepOut o;
     o.rew = 0.0f; o.ep_ret_done = 0.0f; o.prog = 0;
     o.reset = o.timeout = o.did_reset = o.static_dirty = o.fault_active = o.crash_dist = o.crash_z = o.landed_episode = false;
-    float* s_obs = s_P;                                  // reused: [kEkfBlock][13] observation tile
-    __syncthreads();                                     // every thread is done with its covariance column, drain has read the tile
+    float* s_obs = s_P;                                  // reused: the warp's [32][13] observation rows
+    __syncwarp();                                        // every lane is done with its covariance column, the drain has read the tile
     if (valid) {
         Env e;
         unpack(L, e);
@@ -311,18 +317,18 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
         if (io.timeout) io.timeout[i] = o.timeout ? 1 : 0;
         if (io.ep_ret) io.ep_ret[i] = o.ep_ret_done;
 #pragma unroll
-        for (int j = 0; j < 13; ++j) s_obs[tid * 13 + j] = o.obs[j];
+        for (int j = 0; j < 13; ++j) s_obs[lane * 13 + j] = o.obs[j];
     }
     fence_proxy_async_smem();
-    __syncthreads();
-    {
-        float* dst = io.obs + base * 13;
-        const int nflt = n_here * 13;
+    __syncwarp();
+    if (wl > 0) {
+        float* dst = io.obs + wbase * 13;                // 32 x 13 x 4 B per warp: every warp's slice starts on a 16-byte boundary
+        const int nflt = (wl < 32 ? wl : 32) * 13;
         if ((nflt & 3) == 0) {
-            if (tid == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
+            if (lane == 0) bulk_store_s2g(dst, s_obs, (uint32_t)nflt * 4u);
         } else {
 #pragma unroll 1
-            for (int k = tid; k < nflt; k += kEkfBlock) dst[k] = s_obs[k];
+            for (int k = lane; k < nflt; k += 32) dst[k] = s_obs[k];
         }
     }
     // step counter: the launch retires one unit per 128-env tile in total -- block b accounts for the tiles that END in its env range
@@ -331,10 +337,10 @@ ekf_lee_fused_kernel(const __grid_constant__ DevCfg c, const Planes pl, const Ek
     // release the tile (tile_chain.cuh): every bulk store of this CTA has completed, every thread's plain stores are ordered
     // before the barrier, then one fence + release store by the leader
     if (!chain_words) {
-        if (tid == 0) bulk_wait_read_all();
+        if (lane == 0) bulk_wait_read_all();
         return;
     }
-    if (tid < 81) { bulk_wait_all(); fence_proxy_async_all(); }
+    if (lane == 0) { bulk_wait_all(); fence_proxy_async_all(); }
     __syncthreads();
     if (tid == 0) { __threadfence(); st_release_u64(seq + 1, step + 1ull); }
 }
@@ -356,11 +362,13 @@ static int ozl_ekf_lee_block(const ozl_env* env, int64_t n) {
     return 96;
 }
 
-// 2-D tensor map over the caller's [81][N] covariance planes, box = [81][block] (cached in the handle: the pointer is fixed per task).
+// 2-D tensor map over the caller's [81][N] covariance planes, box = [81][32] = one warp's envs (cached in the handle: the pointer is
+// fixed per task).
 // Returns 0 when env->pv_tmap is valid for (P, block).
-static int ozl_encode_pv_tmap(ozl_env* env, const float* P, int64_t n, int block) {
+static int ozl_encode_pv_tmap(ozl_env* env, const float* P, int64_t n) {
+    const int block = 32;                                         // one box per warp
     if (env->pv_tmap_ptr == P && env->pv_tmap_block == block) return 0;
-    if (block > 256 || n < block) return 1;                       // box dimensions are limited to 256 elements
+    if (n < block) return 1;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -418,7 +426,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     for (int k = 0; k < 3; ++k) { a.g.kP[k] = in->gains16[k]; a.g.kV[k] = in->gains16[3 + k]; a.g.kR[k] = in->gains16[6 + k]; a.g.kO[k] = in->gains16[9 + k]; }
     for (int k = 0; k < 4; ++k) a.g.scale[k] = in->gains16[12 + k];
     // TMA path: every [k][N] plane slice of a block must start on a 16-byte boundary and be a multiple of 16 bytes long
-    int use_tma = (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0);       // 1: 81 plane copies (1-D), 2: one tensor-map copy
+    int use_tma = 0;                                                        // 1: per-warp tensor-map copies of the covariance tile
     HuskyArgs h{};
     if (husky) {
         if (ozl_fill_husky_args(husky, h, "ozl_ekf_lee_landed_step")) return 1;
@@ -439,7 +447,7 @@ static int launch_ekf_lee(ozl_env* env, const ozl_ekf_lee_args* in, const ozl_hu
     {
         static int tmap_mode = -1;                                  // OZL_EKF_TMAP=0: keep the 81 plane copies
         if (tmap_mode < 0) { const char* v = getenv("OZL_EKF_TMAP"); tmap_mode = v ? atoi(v) : 1; }
-        if (use_tma && tmap_mode && ozl_encode_pv_tmap(env, a.pv_P, a.n, block) == 0) use_tma = 2;
+        if (tmap_mode && (a.n % 4 == 0) && (((uintptr_t)a.pv_P & 15) == 0) && ozl_encode_pv_tmap(env, a.pv_P, a.n) == 0) use_tma = 1;
     }
     const long long slots = (long long)env->sm_count * ekf_minb(block);
     const bool may_chain = husky && env->use_pdl && (env->chain_mode == 2 || (env->chain_mode == 1 && (long long)grid > slots));
