@@ -448,6 +448,24 @@ typedef struct ozl_quadcopter_args {
 } ozl_quadcopter_args;
 int ozl_quadcopter_step(const ozl_quadcopter_args* args, void* stream);
 
+/* Observation / action noise of the reference's domain randomisation (the `noise_lambda`s of tasks/base/vec_task.py:576-646),
+ * applied in place to an [n,width] f32 tensor:
+ *     gaussian  out = op(x, (corr * b_corr + a_corr) + randn * b + a)        a = mu,  b = var  (used as the std factor, as there)
+ *     uniform   out = op(x, (corr * (b_corr - a_corr) + a_corr) + rand * (b - a) + a)       a = lo,  b = hi
+ * op = + (additive) or * (scaling); `corr` is a standard normal drawn once per randomisation event (`corr_epoch`) and kept until the
+ * next one, randn / rand are fresh every `step`.  The schedule (linear / constant) is applied by the caller when the event happens
+ * (ouzelum_b200.vec_task.VecTask.apply_randomizations).  `step_ptr` (optional): a device step-counter record; the kernel then
+ * uses its value + `step_offset` instead of `step` (CUDA-graph capturable).  `clip` > 0 clamps the result to [-clip, clip].
+ * `which`: 0 observations, 1 actions (separate random streams). */
+typedef struct ozl_noise_lambda {
+    int32_t distribution;         /* OZL_DR_GAUSSIAN or OZL_DR_UNIFORM */
+    int32_t operation;            /* OZL_DR_ADDITIVE or OZL_DR_SCALING */
+    float a, b, a_corr, b_corr;
+} ozl_noise_lambda;
+int ozl_noise_lambda_apply(int64_t n, int32_t width, float* tensor, const ozl_noise_lambda* spec, float clip, uint64_t seed,
+                           uint64_t step, const uint64_t* step_ptr, int64_t step_offset, uint64_t corr_epoch, int64_t env_id_base,
+                           int32_t which, void* stream);
+
 /* A stand-alone device step counter for kernels without an env handle: 16 bytes of caller-owned device memory (16-byte aligned),
  * the same record ozl_step_counter_ptr describes.  `n_envs` fixes how many 128-env blocks retire a work unit per step. */
 int ozl_step_record_init(uint64_t* record_dev, int64_t n_envs, uint64_t step, void* stream);

@@ -140,6 +140,12 @@ class OzlQuadcopterArgs(C.Structure):
     ]
 
 
+class OzlNoiseLambda(C.Structure):
+    """Mirror of `struct ozl_noise_lambda` (include/ouzelum_b200.h)."""
+    _fields_ = [("distribution", C.c_int32), ("operation", C.c_int32), ("a", C.c_float), ("b", C.c_float),
+                ("a_corr", C.c_float), ("b_corr", C.c_float)]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ozl_abi_version": (C.c_int, []),
@@ -201,6 +207,8 @@ _SIGS = {
     "ozl_pomdp_observation_dev": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P, C.c_int64, C.c_int32,
                                             _P, _P, _P]),
     "ozl_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "ozl_noise_lambda_apply": (C.c_int, [C.c_int64, C.c_int32, _P, C.POINTER(OzlNoiseLambda), C.c_float, C.c_uint64, C.c_uint64, _P,
+                                         C.c_int64, C.c_uint64, C.c_int64, C.c_int32, _P]),
 }
 
 

@@ -173,6 +173,55 @@ __global__ void pomdp_kernel(int64_t n, int d, int mode, float flicker_p, float 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ DR noise lambdas
+// The observation / action noise of the reference's domain randomisation (tasks/base/vec_task.py:576-646): per element
+//     gaussian:  out = op(x, (corr * var_corr + mu_corr) + randn * var + mu)
+//     uniform:   out = op(x, (corr * (hi_corr - lo_corr) + lo_corr) + rand * (hi - lo) + lo)
+// with `corr` a standard-normal sample drawn ONCE per randomisation event and kept until the next one (params['corr'], :612-616,
+// :637-641) and randn / rand fresh every step; op = + or *.  The schedule (:583-609, :621-635) is applied by the host when the
+// event happens, so a / b / a_corr / b_corr arrive already scaled.  Draws: philox(seed, env, step, P_LAMBDA + 16 which + j/4) for the
+// fresh sample and philox(seed, env, corr_epoch, P_LAMBDA_CORR + 16 which + j/4) for the correlated one (stateless: the same
+// value every step of the event); normals by Box-Muller in float64 from the 24-bit uniforms (u1 in (0,1]), rounded to float32 once.
+// `clip` > 0 clamps the result (the observation clamp of vec_task.py:353 comes after the noise).
+constexpr uint32_t P_LAMBDA = 32, P_LAMBDA_CORR = 64;
+__device__ __forceinline__ void box_muller4(const uint4 r, float z[4]) {
+    const double k = 5.9604644775390625e-08, two_pi = 6.283185307179586;
+    const double u1 = ((double)(r.x >> 8) + 1.0) * k, u2 = (double)(r.y >> 8) * k;
+    const double u3 = ((double)(r.z >> 8) + 1.0) * k, u4 = (double)(r.w >> 8) * k;
+    const double ra = sqrt(-2.0 * log(u1)), rb = sqrt(-2.0 * log(u3));
+    double sa, ca, sb, cb;
+    sincos(two_pi * u2, &sa, &ca);
+    sincos(two_pi * u4, &sb, &cb);
+    z[0] = (float)(ra * ca); z[1] = (float)(ra * sa); z[2] = (float)(rb * cb); z[3] = (float)(rb * sb);
+}
+struct NoiseLambda { int dist, op; float a, b, a_corr, b_corr; };
+__global__ void noise_lambda_kernel(int64_t n, int width, float* __restrict__ x, const NoiseLambda s, float clip, uint64_t seed,
+                                    uint64_t step, const unsigned long long* __restrict__ step_ptr, long long step_offset,
+                                    uint64_t corr_epoch, uint32_t env_id_base, uint32_t which) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (step_ptr) step = (uint64_t)((long long)read_step(step_ptr) + step_offset);
+    const uint32_t genv = env_id_base + (uint32_t)i;
+    const bool gauss = s.dist == OZL_DR_GAUSSIAN;
+    const float corr_scale = gauss ? s.b_corr : (s.b_corr - s.a_corr), scale = gauss ? s.b : (s.b - s.a);
+    for (int j0 = 0; j0 < width; j0 += 4) {
+        const uint32_t g = (uint32_t)(j0 >> 2) + 16u * which;
+        const uint4 r = draw(seed, genv, step, P_LAMBDA + g), rc = draw(seed, genv, corr_epoch, P_LAMBDA_CORR + g);
+        float zc[4], zf[4];
+        box_muller4(rc, zc);
+        if (gauss) box_muller4(r, zf);
+        else { zf[0] = u01(r.x); zf[1] = u01(r.y); zf[2] = u01(r.z); zf[3] = u01(r.w); }
+        for (int j = 0; j < 4 && j0 + j < width; ++j) {
+            const float corr = zc[j] * corr_scale + s.a_corr;
+            const float noise = (corr + zf[j] * scale) + s.a;
+            float v = x[i * width + j0 + j];
+            v = s.op == OZL_DR_ADDITIVE ? v + noise : v * noise;
+            if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+            x[i * width + j0 + j] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ E3 glue
 // Sensor front-end of EKFLeeLanded.pre_physics_step (tasks/ekf_lee_landed.py:345-346,366-375,397-406): from the true root
 // state builds, per env, sensors[16] = accel(3) | gyr(3) | ang xyzw(4) | pos(3) | vel(3), optionally through the
@@ -406,4 +455,22 @@ extern "C" int ozl_episode_stats(int64_t n, const float* rew, const int64_t* don
     if (!rew || !done || !ep_ret || !ep_len || !ret_out || !len_out) return set_error("ozl_episode_stats: NULL buffer");
     episode_stats_kernel<<<nblk(n, 256), 256, 0, st>>>(n, rew, done, ep_ret, ep_len, ret_out, len_out);
     return check_cuda(cudaGetLastError(), "episode_stats_kernel");
+}
+
+
+extern "C" int ozl_noise_lambda_apply(int64_t n, int32_t width, float* tensor, const ozl_noise_lambda* spec, float clip, uint64_t seed,
+                                      uint64_t step, const uint64_t* step_ptr, int64_t step_offset, uint64_t corr_epoch,
+                                      int64_t env_id_base, int32_t which, void* stream) {
+    if (!tensor || !spec) return set_error("ozl_noise_lambda_apply: NULL argument");
+    if (n <= 0 || width <= 0 || width > 64) return set_error("ozl_noise_lambda_apply: n = %lld, width = %d (1..64)", (long long)n, width);
+    if (spec->distribution != OZL_DR_GAUSSIAN && spec->distribution != OZL_DR_UNIFORM)
+        return set_error("ozl_noise_lambda_apply: distribution must be gaussian or uniform (vec_task.py:586,618)");
+    if (spec->operation != OZL_DR_ADDITIVE && spec->operation != OZL_DR_SCALING)
+        return set_error("ozl_noise_lambda_apply: operation must be additive or scaling");
+    if (which != 0 && which != 1) return set_error("ozl_noise_lambda_apply: which must be 0 (observations) or 1 (actions)");
+    NoiseLambda s{spec->distribution, spec->operation, spec->a, spec->b, spec->a_corr, spec->b_corr};
+    noise_lambda_kernel<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        n, width, tensor, s, clip, seed, step, reinterpret_cast<const unsigned long long*>(step_ptr), (long long)step_offset, corr_epoch,
+        (uint32_t)env_id_base, (uint32_t)which);
+    return check_cuda(cudaGetLastError(), "noise_lambda_kernel");
 }
