@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ouzelum_b200", "libouzelum_b200.so")
-COLS = [("UBLKCP", ("UBLKCP",)), ("SYNCS", ("SYNCS",)), ("LDG", ("LDG",)), ("STG", ("STG",)), ("LDS", ("LDS",)), ("STS", ("STS",)),
+COLS = [("UBLKCP", ("UBLKCP",)), ("UTMALDG+UTMASTG", ("UTMALDG", "UTMASTG")), ("SYNCS", ("SYNCS",)), ("LDG", ("LDG",)), ("STG", ("STG",)), ("LDS", ("LDS",)), ("STS", ("STS",)),
         ("MUFU", ("MUFU",)), ("FFMA", ("FFMA",)), ("FMUL+FADD", ("FMUL", "FADD")), ("DFMA+DMUL+DADD", ("DFMA", "DMUL", "DADD")),
         ("RED/ATOM", ("RED", "REDG", "ATOMG", "ATOM"))]
 
@@ -27,7 +27,7 @@ def main(out):
             cur["_total"] += 1
     with open(out, "w") as f:
         f.write("# SASS evidence (cuobjdump -sass ouzelum_b200/libouzelum_b200.so, sm_100a)\n\n"
-                "Blackwell/Hopper async-copy and barrier mnemonics per kernel (TMA bulk copy = `UBLKCP`, mbarrier = `SYNCS`; no `HMMA`/`UTC*MMA`: "
+                "Blackwell/Hopper async-copy and barrier mnemonics per kernel (TMA 1-D bulk copy = `UBLKCP`, 2-D tensor-map copy = `UTMALDG` / `UTMASTG`, mbarrier = `SYNCS`; no `HMMA`/`UTC*MMA`: "
                 "nothing on this path is a dense contraction).\n\n")
         f.write("| kernel | SASS instructions | " + " | ".join(c for c, _ in COLS) + " |\n|---|---:|" + "---:|" * len(COLS) + "\n")
         for name, c in kernels.items():
