@@ -44,7 +44,8 @@ def config_of(envs_per_gpu, world):
                   "behind a GPU pre-roll that lets the host finish enqueueing before the first event fires",
             "parallelism": f"env-sharded x{world}, no data-path collective; the 16-double metrics vector is read every {METRICS_EVERY} steps "
                            "INSIDE the timed graph and, for N > 1, summed over the ranks inside the same graph (NVLink peer-memory "
-                           "exchange issued by the metrics kernel itself; `--metrics-collective nccl`: NCCL all-reduce on a side stream)"}
+                           "exchange issued by the metrics kernel itself, on a side stream forked inside the graph; "
+                           "`--metrics-collective nccl`: NCCL all-reduce on a side stream)"}
 
 
 def parse():
@@ -58,8 +59,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-side-configs", action="store_true")
-    p.add_argument("--metrics-collective", default="peer", choices=["peer", "nccl"],
-                   help="N > 1: how the metrics vector is summed over the ranks inside the timed graph")
+    p.add_argument("--metrics-collective", default="peer", choices=["peer", "peer-inline", "nccl", "none"],
+                   help="N > 1: how the metrics vector is summed over the ranks inside the timed graph ('none': diagnostic -- "
+                        "every rank only reads its own vector, as a one-GPU run does)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--roofline-only", action="store_true", help="profiling aid: run only the 1 Mi-env roofline region")
     return p.parse_args()
@@ -298,8 +300,16 @@ def run_ours(args):
     # side stream for comparison
     collective = "none"
     peer = None
+    peer_on_side = False
     if world > 1:
         collective = args.metrics_collective
+        # "peer": the exchange kernels run on a side stream forked inside the graph ("issued on a side stream ... consumed
+        # asynchronously"), off the chain of step launches -- K = 20, 2 GPUs: 90.2 us for the 20 steps vs 92.2-94.2 with the kernels in
+        # the chain ("peer-inline") and 88.1 without any collective.  Every step of this bench runs on its own handle (rotating
+        # shards), so the side-stream read of a handle's metrics never overlaps a step on that handle.
+        peer_on_side = collective == "peer"
+        if collective == "peer-inline":
+            collective = "peer"
         if collective == "peer":
             from ouzelum_b200.dist import PeerMetrics
             try:
@@ -333,6 +343,12 @@ def run_ours(args):
         m = metrics_ring[(k // METRICS_EVERY) % n_reads]
         if peer is not None:
             # ONE launch: read + 16-byte stores into every rank's mailbox over NVLink; the sum of the previous exchange is folded in
+            if peer_on_side:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    peer.push(shards[k % S][0], local=m, prev_sum=metrics_sum)
+                forked[0] = True
+                return
             peer.push(shards[k % S][0], local=m, prev_sum=metrics_sum)
             return
         shards[k % S][0].metrics(clear=False, out=m)
@@ -354,10 +370,13 @@ def run_ours(args):
                 step_fn(k)
                 if extra is not None and (k % METRICS_EVERY) == METRICS_PHASE:
                     extra(k)
+            if peer is not None and extra is not None and peer_on_side and forked[0]:
+                with torch.cuda.stream(side):
+                    peer.sum(shards[0][0], out=metrics_sum)
             if forked[0]:
                 torch.cuda.current_stream().wait_stream(side)     # join the side stream the all-reduces were forked to
                 forked[0] = False
-            if peer is not None and extra is not None:
+            if peer is not None and extra is not None and not peer_on_side:
                 peer.sum(shards[0][0], out=metrics_sum)           # the last exchange of the capture is summed inside it
         return g_
 
@@ -691,7 +710,7 @@ def run_ours(args):
             "clocks": clocks.result(),
             "e2e": e2e, "gpu_launches": K + n_metric_reads + n_peer_sums,
             "gpu_launches_note": f"{K} quad_step_kernel<128> + {n_metric_reads} "
-                                 + ("metrics_push_kernel (read + NVLink peer stores)" if collective == "peer" else "metrics_read_kernel")
+                                 + ("metrics_push_kernel (read + NVLink peer stores" + (", side stream)" if peer_on_side else ")") if collective == "peer" else "metrics_read_kernel")
                                  + (f" + {n_peer_sums} metrics_sum_kernel" if n_peer_sums else "")
                                  + " per rank inside the timed region"
                                  + (f" (+ {n_metric_reads} NCCL all-reduce kernels, library)" if nccl_in_graph else ""),
