@@ -200,6 +200,7 @@ extern "C" int ozl_metrics_xchg_ipc_handle(ozl_metrics_xchg* x, void* handle64) 
 
 extern "C" int ozl_metrics_xchg_connect_ipc(ozl_metrics_xchg* x, const void* handles64xWorld) {
     if (!x || !handles64xWorld) return set_error("ozl_metrics_xchg_connect_ipc: NULL argument");
+    if (getenv("OZL_XCHG_FAIL_IPC")) return set_error("ozl_metrics_xchg_connect_ipc: refused (OZL_XCHG_FAIL_IPC is set: fallback test)");
     if (check_cuda(cudaSetDevice(x->device), "cudaSetDevice")) return 1;
     for (int r = 0; r < x->world; ++r) {
         if (r == x->rank || x->peer[r]) continue;
