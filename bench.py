@@ -526,8 +526,13 @@ def run_ours(args):
 
         e2e_ranks = {}
 
+        # untimed host-path warm-up: like the headline's max(W, S) pre-roll.  The host <-> device round trip keeps getting faster for
+        # the first ~200 steps (8 ms) of a run -- measured at K = 20: 40.6-41.2 us per step after 5 warm-up steps, 39.8-42.0 after 64,
+        # 37.7 after 256 = the K = 1000 figure (profiles/r02an_*) -- so the steady state is what gets timed; the count is in the line
+        W_e2e = max(W, int(os.environ.get("OZL_BENCH_E2E_WARMUP", "256")))
+
         def timed(fn, tag=None):
-            for k in range(W):
+            for k in range(W_e2e):
                 fn(k)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -580,7 +585,7 @@ def run_ours(args):
         for eh, _, _ in halves:
             eh.step_host_wait()
             eh.close()
-        e2e = {"value": v_host, "unit": UNIT,
+        e2e = {"value": v_host, "unit": UNIT, "warmup_steps": W_e2e,
                "h2d_bytes_per_step": world * h_act[0].numel() * 4,
                "d2h_bytes_per_step": world * (n * 13 * 4 + n * 4 + n * 8 + n),
                "api": "ouzelum_b200.make(...).step_host(pinned actions) -> pinned (obs f32 [N,13], reward f32 [N], reset int64 [N]; + the same flags as u8): one launch, zero-copy PCIe reads/writes inside the kernel, stream sync",
