@@ -26,8 +26,9 @@
 extern "C" {
 #endif
 
-#define OZL_ABI_VERSION 3   /* 3: ozl_cfg.dr[] (domain-randomisation schema), per-env yaw_km (params8), wrench_warmup_steps,
-                               ozl_ekf_lee_args.num_envs_total, i64 reset mirror in ozl_host_io */
+#define OZL_ABI_VERSION 4   /* 3: ozl_cfg.dr[] (domain-randomisation schema), per-env yaw_km (params8), wrench_warmup_steps,
+                               ozl_ekf_lee_args.num_envs_total, i64 reset mirror in ozl_host_io
+                               4: (additive) ozl_metrics_xchg_* / ozl_metrics_push / ozl_metrics_sum, ozl_noise_lambda_apply */
 
 /* sensor-fault model of isaacgymenvs/utils/POMDP.py:4-42 */
 enum { OZL_POMDP_NONE = 0, OZL_POMDP_FLICKER = 1, OZL_POMDP_NOISE = 2, OZL_POMDP_FLICKER_NOISE = 3 };
