@@ -57,7 +57,8 @@ struct EkfLeeArgs {
 };
 
 // Envs per CTA: 64 (8 CTAs / SM), 96 (5), 128 (4), 256 (2) or 512 (1) at 128 registers per thread.  Measured on B200 at config 3
-// (65536 envs, one wave): 96 -> 27.1 us, 128 -> 28.4 us, 64 -> 29.4 us, 256 -> +0.1 us over 128, 512 -> +1.3 us.  65536 envs
+// (65536 envs, one wave): 96 -> 27.1 us, 128 -> 28.4 us, 64 -> 29.4 us, 256 -> +0.1 us over 128, 512 -> +1.3 us.  (Final kernel, warp-private
+// tiles: 96 -> 23.8 us, 64 -> 24.3 us, 128 -> 24.7 us, 32 -> 26.5 us.)  65536 envs
 // are 443 envs per SM: with 128-env CTAs the SMs hold 3 or 4 of them (12 or 16 warps) and the launch lasts as long as the SMs
 // with 16; 96-env CTAs spread the same envs as 4 or 5 CTAs (12 or 15 warps).  See ozl_ekf_lee_block().
 constexpr int ekf_minb(int block) { return block <= 64 ? 8 : (block <= 96 ? 5 : (block <= 128 ? 4 : (block <= 256 ? 2 : 1))); }
