@@ -639,7 +639,7 @@ def run_ours(args):
         ach = ALG_BYTES_PER_ENV_STEP * nb / per_launch_s / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                    "kernel": "quad_step_tma_kernel (persistent, TMA-pipelined; the same step as quad_step_kernel<128> which serves N < ~400k)", "n_envs": nb, "launch_us": per_launch_s * 1e6,
+                    "kernel": "quad_step_tma_kernel (persistent, TMA-pipelined; the same step as quad_step_kernel<128> which serves one-wave sizes, N <= 132608)", "n_envs": nb, "launch_us": per_launch_s * 1e6,
                     "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "peak_source": peak_src,
                     "l2": "inputs (311 MB/launch) exceed the 126 MB L2; no flush; 50 launches replayed from a CUDA graph, one event pair",
                     "env_steps_per_sec_at_this_size": nb / per_launch_s}

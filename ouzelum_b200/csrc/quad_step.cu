@@ -726,13 +726,18 @@ extern "C" int ozl_create(const ozl_cfg* cfg, int device, ozl_env** out) {
     derive_dev_cfg(*cfg, e->dev);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    {   // switch to the TMA-pipelined kernel once every resident CTA slot gets ~4.25 tiles (measured crossover on B200, final
-        // kernels: generic 15.0 vs 16.0 us at 262144 envs, 21.5 vs 21.7 us at 393216, 31.2 vs 27.8 us at 524288)
+    {   // switch to the persistent TMA-pipelined kernel as soon as the generic kernel would need a second wave of CTAs (7 x 128-env
+        // CTAs per SM are resident: 1036 tiles = 132608 envs on 148 SMs).
+        // Measured on B200 with the round-2 kernels (profiles/r02at_sizes_*.jsonl; us per step, generic vs TMA):
+        //   131072 envs  warm 8.09 vs 8.86, cold  9.78 vs  9.68      196608  warm 11.47 vs 11.16, cold 15.21 vs 11.98
+        //   262144 envs  warm 13.7 vs 13.6, cold 18.33 vs 15.21      393216  warm 19.92 vs 18.38, cold 24.83 vs 21.96
+        //   163840 envs (1280 tiles, a second generic wave of 244 CTAs): generic warm 10.29, cold 13.51; 180224 envs on the TMA kernel 10.34 / 11.16
+        // (round 1's kernels crossed over at ~400k envs; the lighter integrator moved the crossover down)
         // (override: OZL_TMA_MIN_TILES, 0 = never)
         const char* pv = getenv("OZL_PDL");
         e->use_pdl = pv ? atoi(pv) : 1;
         const char* ev = getenv("OZL_TMA_MIN_TILES");
-        e->tma_min_tiles = ev ? atoll(ev) : (17ll * prop.multiProcessorCount * OZL_TMA_MINB) / 4;
+        e->tma_min_tiles = ev ? atoll(ev) : 7ll * prop.multiProcessorCount + 1;
     }
     const size_t n = (size_t)cfg->num_envs;
     const size_t tiles = (n + kTile - 1) / kTile;
