@@ -66,6 +66,31 @@ def test_one_million_envs_tma_vs_generic_vs_c_oracle():
     assert a_sim.step_count == b_sim.step_count == steps
 
 
+def test_default_kernel_selection_just_above_one_wave_equals_generic_kernel():
+    """The persistent TMA-pipelined kernel takes over as soon as the generic kernel would need a second wave of CTAs (132608 envs on
+    148 SMs).  At a ragged size just above that -- the smallest grid the TMA kernel serves by default: ~1.4 tiles per persistent CTA --
+    the default handle must agree bit for bit with a handle forced onto the generic kernel."""
+    from ouzelum_b200 import _lib
+    from ouzelum_b200.sim import QuadSim
+    n, steps = 133000 + 41, 30
+    kw = dict(seed=77, fault_mode=1, dr_enable=1, max_episode_length=13)
+    os.environ.pop("OZL_TMA_MIN_TILES", None)
+    d_sim, g_sim = QuadSim(_lib.default_cfg(n, **kw), DEV), _mk(n, False, **kw)
+    a, b = _bufs(n), _bufs(n)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for t in range(steps):
+        act = torch.rand(n, 4, device=DEV, generator=g) * 2 - 1
+        d_sim.step(act, a["obs"], a["rew"], a["reset"], a["progress"], a["timeout"], a["ep_ret"])
+        g_sim.step(act, b["obs"], b["rew"], b["reset"], b["progress"], b["timeout"], b["ep_ret"])
+        for k in ("obs", "rew", "reset", "progress", "timeout", "ep_ret"):
+            assert torch.equal(a[k], b[k]), f"default vs generic differ in {k} at step {t}"
+    sa, sb = d_sim.get_state(), g_sim.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    np.testing.assert_array_equal(d_sim.metrics().cpu().numpy()[8:16], g_sim.metrics().cpu().numpy()[8:16])
+    assert d_sim.step_count == g_sim.step_count == steps
+
+
 def test_sharding_is_pure_slicing_at_scale():
     n, parts, steps = 1 << 19, 4, 12
     kw = dict(seed=11, fault_mode=1, dr_enable=1)
