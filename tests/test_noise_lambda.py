@@ -10,37 +10,23 @@ from oracle import noise_lambda as nl
 
 
 def _reference_lines(p, last_step):
-    """vec_task.py:577-635, copied as arithmetic (the reference needs Isaac Gym to reach these lines)."""
-    dist, op_type = p["distribution"], p["operation"]
-    sched_type = p["schedule"] if "schedule" in p else None
-    sched_step = p["schedule_steps"] if "schedule" in p else None
-    if sched_type == 'linear':
-        sched_scaling = 1.0 / sched_step * min(last_step, sched_step)
-    elif sched_type == 'constant':
-        sched_scaling = 0 if last_step < sched_step else 1
-    else:
-        sched_scaling = 1
-    if dist == 'gaussian':
-        mu, var = p["range"]
-        mu_corr, var_corr = p.get("range_correlated", [0., 0.])
-        if op_type == 'additive':
-            mu *= sched_scaling; var *= sched_scaling; mu_corr *= sched_scaling; var_corr *= sched_scaling
-        elif op_type == 'scaling':
-            var = var * sched_scaling
-            mu = mu * sched_scaling + 1.0 * (1.0 - sched_scaling)
-            var_corr = var_corr * sched_scaling
-            mu_corr = mu_corr * sched_scaling + 1.0 * (1.0 - sched_scaling)
-        return mu, var, mu_corr, var_corr
-    lo, hi = p["range"]
-    lo_corr, hi_corr = p.get("range_correlated", [0., 0.])
-    if op_type == 'additive':
-        lo *= sched_scaling; hi *= sched_scaling; lo_corr *= sched_scaling; hi_corr *= sched_scaling
-    elif op_type == 'scaling':
-        lo = lo * sched_scaling + 1.0 * (1.0 - sched_scaling)
-        hi = hi * sched_scaling + 1.0 * (1.0 - sched_scaling)
-        lo_corr = lo_corr * sched_scaling + 1.0 * (1.0 - sched_scaling)
-        hi_corr = hi_corr * sched_scaling + 1.0 * (1.0 - sched_scaling)
-    return lo, hi, lo_corr, hi_corr
+    """What tasks/base/vec_task.py:577-635 computes for one `observations` / `actions` block, written independently of the oracle (the
+    reference needs Isaac Gym to reach these lines, so they cannot be executed here): the schedule factor s (:583-590), then for the
+    `additive` operation all four numbers times s (:596-600, :623-627), for `scaling` every mean / bound blended towards 1 with s and
+    every gaussian spread times s (:601-609, :628-632)."""
+    kind = p.get("schedule")
+    steps = p.get("schedule_steps")
+    s = {None: lambda: 1, "linear": lambda: 1.0 / steps * min(last_step, steps),
+         "constant": lambda: 0 if last_step < steps else 1}[kind]()
+    first, second = p["range"]
+    cfirst, csecond = p.get("range_correlated", [0., 0.])
+    vals = [first, second, cfirst, csecond]
+    if p["operation"] == "additive":
+        return tuple(v * s for v in vals)
+    towards_one = lambda v: v * s + 1.0 * (1.0 - s)
+    if p["distribution"] == "gaussian":                     # (mu, var): the mean is blended, the spread is scaled
+        return (towards_one(first), second * s, towards_one(cfirst), csecond * s)
+    return tuple(towards_one(v) for v in vals)             # uniform (lo, hi): both bounds are blended
 
 
 BLOCKS = [
